@@ -1,0 +1,535 @@
+"""b200 stencil IR -> sm_100a CUDA source + launch plan.
+
+This is the backend code generator of the `b200` entry: the component that stands in for the
+reference's GridTools C++ generator (reference: gtc/gtcpp/gtcpp_codegen.py:37-331,
+backend/gtcpp_backend.py:35-62) — written from scratch, emitting plain SIMT CUDA kernels, one per
+`computation` block (or per group of horizontal executions that can run without a grid-wide
+barrier), instead of GridTools template expressions.
+
+Two kernel families are emitted:
+
+* ``par``  PARALLEL vertical loops: one thread per (i, j) point, K from ``blockIdx.z``; the loop's
+  sections become branches on ``k``.  Horizontal executions are fused into one kernel as long as no
+  field written by an earlier execution is read at a horizontal offset by a later one (that needs a
+  plane-wide barrier -> next kernel); surviving temporaries live in backend-owned scratch.
+* ``seq``  FORWARD/BACKWARD vertical loops: one thread per (i, j) column, the K loop stays inside the
+  thread and sections become consecutive sub-loops.  Loops whose temporaries are read at horizontal
+  offsets in the same level fall back to level-by-level ``par`` launches.
+
+The tiled/streaming generator for multi-stage PARALLEL blocks lives in `codegen_stream.py` and is
+tried first by `generate()`; everything it cannot handle comes here.
+
+Semantics follow the `numpy` backend (the oracle), see SURVEY.md §9 / oracle/numpy_oracle.py.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+from . import ir as b2ir
+
+CT = b2ir.CTYPE
+
+_FUNC = {
+    "abs": "abs_", "min": "min_", "max": "max_", "mod": "mod_", "sin": "sin_", "cos": "cos_",
+    "tan": "tan_", "arcsin": "asin_", "arccos": "acos_", "arctan": "atan_", "sinh": "sinh_",
+    "cosh": "cosh_", "tanh": "tanh_", "arcsinh": "asinh_", "arccosh": "acosh_", "arctanh": "atanh_",
+    "sqrt": "sqrt_", "pow": "pow_", "exp": "exp_", "log": "log_", "log10": "log10_", "gamma": "gamma_",
+    "cbrt": "cbrt_", "isfinite": "isfinite_", "isinf": "isinf_", "isnan": "isnan_", "floor": "floor_",
+    "ceil": "ceil_", "trunc": "trunc_", "erf": "erf_", "erfc": "erfc_", "round": "round_",
+    "round_away_from_zero": "round_away_",
+}  # fmt: skip
+_CASTFUNC = {"int32": "int32", "int64": "int64", "float32": "float32", "float64": "float64"}
+
+
+class CodegenError(NotImplementedError):
+    pass
+
+
+def literal(value: str, dtype: str) -> str:
+    if dtype == "bool":
+        return "true" if value in ("True", "true", "1") else "false"
+    if dtype.startswith("int"):
+        iv = int(value)
+        if dtype == "int64":
+            return f"({iv}LL)" if iv > -(2**63) else "(-9223372036854775807LL-1)"
+        return f"(({CT[dtype]}){iv})"
+    fv = float(value)
+    if fv != fv:
+        return "(__int_as_float(0x7fc00000))" if dtype == "float32" else "(__longlong_as_double(0x7ff8000000000000LL))"
+    if fv in (float("inf"), float("-inf")):
+        base = "__int_as_float(0x7f800000)" if dtype == "float32" else "__longlong_as_double(0x7ff0000000000000LL)"
+        return f"({'-' if fv < 0 else ''}{base})"
+    if dtype == "float32":
+        import numpy as np
+
+        return f"({float(np.float32(fv)).hex()}f)"
+    return f"({fv.hex()})"
+
+
+class FieldTable:
+    """Index of API fields + temporaries in the kernel argument block."""
+
+    def __init__(self, stencil):
+        self.stencil = stencil
+        self.entries: List[dict] = []
+        self.index: Dict[str, int] = {}
+        for p in stencil["params"]:
+            if p["t"] == "field":
+                self._add(p["name"], p["dtype"], p["dims"], p["data_dims"], "api", None)
+        for t in stencil["temporaries"]:
+            self._add(t["name"], t["dtype"], t["dims"], t["data_dims"], "temp", t["extent"])
+        self.scalars = [p for p in stencil["params"] if p["t"] == "scalar"]
+
+    def _add(self, name, dtype, dims, data_dims, kind, extent):
+        if len(data_dims) > 2:
+            raise CodegenError("b200: more than two data dimensions")
+        self.index[name] = len(self.entries)
+        self.entries.append(
+            {"name": name, "dtype": dtype, "dims": list(dims), "data_dims": list(data_dims), "kind": kind, "extent": extent}
+        )
+
+    def scalar_layout(self) -> Tuple[List[dict], int]:
+        """C layout of the scalar-parameter blob (natural alignment, API order)."""
+        off = 0
+        out = []
+        for p in self.scalars:
+            size = b2ir.ITEMSIZE[p["dtype"]]
+            off = (off + size - 1) // size * size
+            out.append({"name": p["name"], "dtype": p["dtype"], "offset": off})
+            off += size
+        return out, (off + 7) // 8 * 8
+
+
+class ExprGen:
+    """Expression / statement emitter for point-wise (one thread = one (i,j[,k]) point) code."""
+
+    def __init__(self, ft: FieldTable, written: set, *, ivar="i", jvar="j", kvar="k", args="A"):
+        self.ft = ft
+        self.written = written  # fields written by the current kernel (no read-only loads)
+        self.i, self.j, self.k, self.A = ivar, jvar, kvar, args
+        self.locals: Dict[str, str] = {}
+
+    # -- addressing ---------------------------------------------------------------------------
+    def field_ref(self, node, *, for_write=False) -> str:
+        name = node["name"]
+        n = self.ft.index[name]
+        ent = self.ft.entries[n]
+        ct = CT[ent["dtype"]]
+        f = f"{self.A}.f[{n}]"
+        off = node["off"]
+        terms = []
+        if isinstance(off, dict):
+            di = dj = 0
+            if "vk" in off:
+                kexpr = f"b200::clampk((long long){self.k} + (long long)({self.expr(off['vk'])}), {f}.klo, {f}.khi)"
+            else:
+                ak = off["abs_k"]
+                kexpr = f"((long long)({ak if isinstance(ak, int) else self.expr(ak)}))"
+        else:
+            di, dj, dk = off
+            kexpr = f"({self.k}{dk:+d})" if dk else self.k
+        if ent["dims"][0]:
+            terms.append(f"(long long)({self.i}{di:+d})*{f}.s[0]" if di else f"(long long){self.i}*{f}.s[0]")
+        if ent["dims"][1]:
+            terms.append(f"(long long)({self.j}{dj:+d})*{f}.s[1]" if dj else f"(long long){self.j}*{f}.s[1]")
+        if ent["dims"][2]:
+            terms.append(f"(long long){kexpr}*{f}.s[2]")
+        for d, ix in enumerate(node.get("data_index", [])):
+            terms.append(f"(long long)({self.expr(ix)})*{f}.s[{3 + d}]")
+        idx = " + ".join(terms) if terms else "0"
+        return f"(({ct}*){f}.p)[{idx}]"
+
+    def field_load(self, node) -> str:
+        ref = self.field_ref(node)
+        if node["name"] in self.written:
+            return ref
+        ct = CT[self.ft.entries[self.ft.index[node["name"]]]["dtype"]]
+        return f"b200::ldro<{ct}>(&{ref})"
+
+    # -- expressions ----------------------------------------------------------------------------
+    def expr(self, n) -> str:
+        t = n["t"]
+        if t == "field":
+            return self.field_load(n)
+        if t == "scalar":
+            name = n["name"]
+            if name in self.locals:
+                return self.locals[name]
+            return f"{self.A}.p_{name}"
+        if t == "lit":
+            return literal(n["value"], n["dtype"])
+        if t == "iter":
+            axis = {"I": self.i, "J": self.j, "K": self.k}[n["axis"]]
+            return f"(({CT[n['dtype']]}){axis})"
+        if t == "cast":
+            src = n["expr"]
+            if n["dtype"] == "bool" and src["dtype"] != "bool":
+                return f"(({self.expr(src)}) != 0)"
+            return f"(({CT[n['dtype']]})({self.expr(src)}))"
+        if t == "unary":
+            op = n["op"]
+            e = self.expr(n["expr"])
+            if op == "not":
+                return f"(!({e}))"
+            if op == "-":
+                return f"(({CT[n['dtype']]})(-({e})))"
+            return f"(+({e}))"
+        if t == "binary":
+            op = n["op"]
+            a, b = self.expr(n["left"]), self.expr(n["right"])
+            if op in ("and", "or"):
+                return f"(({a}) {'&&' if op == 'and' else '||'} ({b}))"
+            if op in (">", "<", ">=", "<=", "==", "!="):
+                return f"(({a}) {op} ({b}))"
+            dt = n["dtype"]
+            if dt in ("int8", "int16", "bool"):
+                return f"(({CT[dt]})(({a}) {op} ({b})))"
+            if op == "/" and dt.startswith("int"):
+                # NumPy true-divide then store into an integer: truncation toward zero == C division
+                return f"((({b}) == 0) ? ({CT[dt]})0 : ({CT[dt]})(({a}) / ({b})))"
+            return f"(({a}) {op} ({b}))"
+        if t == "ternary":
+            ct = CT[n["dtype"]]
+            return f"(({self.expr(n['cond'])}) ? ({ct})({self.expr(n['true'])}) : ({ct})({self.expr(n['false'])}))"
+        if t == "call":
+            fn = n["func"]
+            args = [self.expr(a) for a in n["args"]]
+            if fn in _CASTFUNC:
+                return f"(({CT[_CASTFUNC[fn]]})({args[0]}))"
+            if fn not in _FUNC:
+                raise CodegenError(f"b200: native function {fn}")
+            call = f"b200::{_FUNC[fn]}({', '.join(args)})"
+            if fn in ("isfinite", "isinf", "isnan"):
+                return call
+            return f"(({CT[n['dtype']]}){call})"
+        raise CodegenError(f"b200: expression {t}")
+
+    # -- statements -----------------------------------------------------------------------------
+    def stmts(self, body, ind: str) -> List[str]:
+        out: List[str] = []
+        for s in body:
+            t = s["t"]
+            if t == "assign":
+                left = s["left"]
+                rhs = self.expr(s["right"])
+                if left["t"] == "scalar":
+                    out.append(f"{ind}{self.locals[left['name']]} = ({CT[left['dtype']]})({rhs});")
+                else:
+                    ct = CT[self.ft.entries[self.ft.index[left['name']]]["dtype"]]
+                    out.append(f"{ind}{self.field_ref(left, for_write=True)} = ({ct})({rhs});")
+            elif t == "mask":
+                out.append(f"{ind}if ({self.expr(s['mask'])}) {{")
+                out += self.stmts(s["body"], ind + "  ")
+                out.append(f"{ind}}}")
+            elif t == "while":
+                out.append(f"{ind}while ({self.expr(s['cond'])}) {{")
+                out += self.stmts(s["body"], ind + "  ")
+                out.append(f"{ind}}}")
+            elif t == "hregion":
+                conds = []
+                for var, n_sym, (lo, hi) in ((self.i, f"{self.A}.g.nI", s["i"]), (self.j, f"{self.A}.g.nJ", s["j"])):
+                    if lo is not None:
+                        conds.append(f"{var} >= {_bound(lo, n_sym)}")
+                    if hi is not None:
+                        conds.append(f"{var} < {_bound(hi, n_sym)}")
+                out.append(f"{ind}if ({' && '.join(conds) if conds else 'true'}) {{")
+                out += self.stmts(s["body"], ind + "  ")
+                out.append(f"{ind}}}")
+            else:
+                raise CodegenError(f"b200: statement {t}")
+        return out
+
+    def he_block(self, he, ind: str, *, guard_extent=True, declare_locals=True) -> List[str]:
+        """One horizontal execution for the current point, guarded by its own block extent."""
+        (ei0, ei1), (ej0, ej1) = he["extent"]
+        out = []
+        A = self.A
+        if guard_extent:
+            out.append(
+                f"{ind}if ({self.i} >= {A}.g.i_lo{ei0:+d} && {self.i} < {A}.g.i_hi{ei1:+d} && "
+                f"{self.j} >= {A}.g.j_lo{ej0:+d} && {self.j} < {A}.g.j_hi{ej1:+d}) {{"
+            )
+        else:
+            out.append(f"{ind}{{")
+        saved = dict(self.locals)
+        if declare_locals:
+            for d in he["locals"]:
+                self.locals[d["name"]] = f"l_{d['name']}"
+                out.append(f"{ind}  {CT[d['dtype']]} l_{d['name']} = ({CT[d['dtype']]})0;")
+        out += self.stmts(he["body"], ind + "  ")
+        out.append(f"{ind}}}")
+        if declare_locals:
+            self.locals = saved
+        return out
+
+
+def _bound(b, n_sym: str) -> str:
+    level, off = b
+    return f"({off})" if level == "start" else f"({n_sym}{off:+d})"
+
+
+def _written_in(hes) -> set:
+    return {a["name"] for he in hes for a in b2ir.field_accesses(he["body"]) if a["write"]}
+
+
+def split_groups(hes: List[dict]) -> List[List[dict]]:
+    """Split a section's horizontal executions where a plane-wide barrier is needed.
+
+    A new kernel starts when an execution reads, at a non-zero IJ offset, a field written earlier in
+    the group (RAW across threads) or writes a field read earlier at a non-zero IJ offset (WAR).
+    """
+    groups: List[List[dict]] = []
+    cur: List[dict] = []
+    written: set = set()
+    read_off: set = set()
+    for he in hes:
+        acc = b2ir.field_accesses(he["body"])
+        raw = any((not a["write"]) and a["name"] in written and b2ir.ij_offset(a["off"]) != (0, 0) for a in acc)
+        war = any(a["write"] and a["name"] in read_off for a in acc)
+        if cur and (raw or war):
+            groups.append(cur)
+            cur, written, read_off = [], set(), set()
+        cur.append(he)
+        written |= {a["name"] for a in acc if a["write"]}
+        read_off |= {a["name"] for a in acc if not a["write"] and b2ir.ij_offset(a["off"]) != (0, 0)}
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def _union_extent(hes) -> List[List[int]]:
+    e = [[0, 0], [0, 0]]
+    for he in hes:
+        for a in range(2):
+            e[a][0] = min(e[a][0], he["extent"][a][0])
+            e[a][1] = max(e[a][1], he["extent"][a][1])
+    return e
+
+
+def _needs_level_sync(loop) -> bool:
+    written, read_off = set(), set()
+    for sec in loop["sections"]:
+        for he in sec["hes"]:
+            for a in b2ir.field_accesses(he["body"]):
+                if a["write"]:
+                    written.add(a["name"])
+                elif b2ir.ij_offset(a["off"]) != (0, 0):
+                    read_off.add(a["name"])
+    return bool(written & read_off)
+
+
+class Generator:
+    """Baseline ("point") generator: always applicable."""
+
+    BLOCK_PAR = (64, 4)
+    BLOCK_SEQ = (64, 2)
+
+    def __init__(self, stencil: Dict[str, Any], options: Optional[Dict[str, Any]] = None):
+        self.st = stencil
+        self.opt = dict(options or {})
+        self.ft = FieldTable(stencil)
+        self.kernels: List[dict] = []
+        self.steps: List[dict] = []
+        self.src: List[str] = []
+
+    # -- argument block ---------------------------------------------------------------------------
+    def args_struct(self) -> str:
+        scal, size = self.ft.scalar_layout()
+        lines = ["struct Args {", "  b200::Geom g;", f"  b200::FieldArg f[{max(1, len(self.ft.entries))}];"]
+        pos = 0
+        pad = 0
+        for s in scal:
+            if s["offset"] > pos:
+                lines.append(f"  char _pad{pad}[{s['offset'] - pos}];")
+                pad += 1
+            lines.append(f"  {CT[s['dtype']]} p_{s['name']};")
+            pos = s["offset"] + b2ir.ITEMSIZE[s["dtype"]]
+        if size > pos:
+            lines.append(f"  char _pad{pad}[{size - pos}];")
+        lines.append("};")
+        return "\n".join(lines)
+
+    # -- kernels ------------------------------------------------------------------------------------
+    def _kname(self, tag: str) -> str:
+        return f"b200_{_cname(self.st['name'])}_{tag}{len(self.kernels)}"
+
+    def emit_par_kernel(self, sections: List[Tuple[list, List[dict]]], *, level_mode=False) -> int:
+        """sections: [(interval, [he...])]; all fused in one kernel, K from blockIdx.z."""
+        name = self._kname("par")
+        all_hes = [he for _, hes in sections for he in hes]
+        eg = ExprGen(self.ft, _written_in(all_hes))
+        ext = _union_extent(all_hes)
+        bx, by = self.BLOCK_PAR
+        L = [f'extern "C" __global__ void __launch_bounds__({bx * by}) {name}(const __grid_constant__ Args A) {{']
+        L.append(f"  const int i = A.g.i_lo + ({ext[0][0]}) + (int)(blockIdx.x * {bx} + threadIdx.x);")
+        L.append(f"  const int j = A.g.j_lo + ({ext[1][0]}) + (int)(blockIdx.y * {by} + threadIdx.y);")
+        L.append("  const int k = A.g.k_lo + (int)blockIdx.z;")
+        for interval, hes in sections:
+            k0 = _bound(interval[0], "A.g.nK")
+            k1 = _bound(interval[1], "A.g.nK")
+            L.append(f"  if (k >= {k0} && k < {k1}) {{")
+            for he in hes:
+                L += eg.he_block(he, "    ")
+            L.append("  }")
+        L.append("}")
+        self.src.append("\n".join(L))
+        k_lo = sections[0][0][0]
+        k_hi = sections[-1][0][1]
+        self.kernels.append(
+            {"name": name, "kind": "par", "block": [bx, by, 1], "extent": ext, "k_lo": k_lo, "k_hi": k_hi, "smem": 0}
+        )
+        return len(self.kernels) - 1
+
+    def emit_seq_kernel(self, loop) -> int:
+        name = self._kname("seq")
+        order = loop["order"]
+        all_hes = [he for sec in loop["sections"] for he in sec["hes"]]
+        eg = ExprGen(self.ft, _written_in(all_hes))
+        ext = _union_extent(all_hes)
+        bx, by = self.BLOCK_SEQ
+        L = [f'extern "C" __global__ void __launch_bounds__({bx * by}) {name}(const __grid_constant__ Args A) {{']
+        L.append(f"  const int i = A.g.i_lo + ({ext[0][0]}) + (int)(blockIdx.x * {bx} + threadIdx.x);")
+        L.append(f"  const int j = A.g.j_lo + ({ext[1][0]}) + (int)(blockIdx.y * {by} + threadIdx.y);")
+        for sec in loop["sections"]:
+            k0 = _bound(sec["interval"][0], "A.g.nK")
+            k1 = _bound(sec["interval"][1], "A.g.nK")
+            if order == "forward":
+                L.append(f"  for (int k = {k0}; k < {k1}; ++k) {{")
+            else:
+                L.append(f"  for (int k = {k1} - 1; k >= {k0}; --k) {{")
+            for he in sec["hes"]:
+                L += eg.he_block(he, "    ")
+            L.append("  }")
+        L.append("}")
+        self.src.append("\n".join(L))
+        self.kernels.append(
+            {"name": name, "kind": "seq", "block": [bx, by, 1], "extent": ext, "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": 0}
+        )
+        return len(self.kernels) - 1
+
+    # -- driver -------------------------------------------------------------------------------------
+    def lower_loop(self, loop) -> None:
+        order = loop["order"]
+        if order == "parallel":
+            grouped = [(sec["interval"], split_groups(sec["hes"])) for sec in loop["sections"]]
+            if all(len(g) == 1 for _, g in grouped):
+                k = self.emit_par_kernel([(iv, g[0]) for iv, g in grouped])
+                self.steps.append({"t": "launch", "kernel": k})
+            else:
+                for iv, groups in grouped:
+                    for g in groups:
+                        k = self.emit_par_kernel([(iv, g)])
+                        self.steps.append({"t": "launch", "kernel": k})
+            return
+        if not _needs_level_sync(loop):
+            k = self.emit_seq_kernel(loop)
+            self.steps.append({"t": "launch", "kernel": k})
+            return
+        # level-by-level fallback: sections in loop order, every group its own kernel
+        secs = []
+        for sec in loop["sections"]:
+            ks = [self.emit_par_kernel([(sec["interval"], g)], level_mode=True) for g in split_groups(sec["hes"])]
+            secs.append({"interval": sec["interval"], "kernels": ks})
+        self.steps.append({"t": "levels", "order": order, "sections": secs})
+
+    def generate(self) -> Tuple[str, Dict[str, Any]]:
+        for loop in self.st["loops"]:
+            self.lower_loop(loop)
+        return self.finish()
+
+    def finish(self) -> Tuple[str, Dict[str, Any]]:
+        scal, scal_size = self.ft.scalar_layout()
+        header = [
+            "// generated by gt4py_b200.codegen — do not edit",
+            f"// stencil: {self.st['name']}",
+            '#include "b200_device.cuh"',
+            "namespace {",
+            self.args_struct(),
+            "}  // namespace",
+            "",
+        ]
+        source = "\n".join(header) + "\n\n".join(self.src) + "\n"
+        plan = {
+            "version": 1,
+            "name": self.st["name"],
+            "fields": [
+                {
+                    "name": e["name"],
+                    "dtype": e["dtype"],
+                    "itemsize": b2ir.ITEMSIZE[e["dtype"]],
+                    "dims": e["dims"],
+                    "data_dims": e["data_dims"],
+                    "kind": e["kind"],
+                    "extent": e["extent"],
+                }
+                for e in self.ft.entries
+            ],
+            "scalars": scal,
+            "scalars_size": scal_size,
+            "kernels": self.kernels,
+            "steps": self.steps,
+        }
+        return source, plan
+
+
+def _cname(name: str) -> str:
+    return "".join(c if c.isalnum() else "_" for c in name)
+
+
+def generate(stencil: Dict[str, Any], options: Optional[Dict[str, Any]] = None) -> Tuple[str, Dict[str, Any]]:
+    """IR -> (CUDA source, launch plan).  Tries the streaming generator first (if enabled)."""
+    options = dict(options or {})
+    if options.get("strategy", "auto") in ("auto", "stream"):
+        try:
+            from . import codegen_stream
+
+            res = codegen_stream.try_generate(stencil, options)
+            if res is not None:
+                return res
+        except ImportError:
+            pass
+        if options.get("strategy") == "stream":
+            raise CodegenError("b200: streaming strategy not applicable to this stencil")
+    return Generator(stencil, options).generate()
+
+
+def plan_to_text(plan: Dict[str, Any]) -> str:
+    """Flat, line-oriented rendering of the launch plan for the C launcher (csrc/launcher.cu)."""
+
+    def b(bound):
+        return f"{0 if bound[0] == 'start' else 1} {bound[1]}"
+
+    L = [f"b200plan {plan['version']}", f"name {plan['name']}"]
+    L.append(f"nfields {len(plan['fields'])}")
+    for f in plan["fields"]:
+        e = f["extent"] or [[0, 0], [0, 0]]
+        dd = f["data_dims"] + [1] * (2 - len(f["data_dims"]))
+        L.append(
+            f"field {f['name']} {1 if f['kind'] == 'temp' else 0} {f['itemsize']} "
+            f"{int(f['dims'][0])} {int(f['dims'][1])} {int(f['dims'][2])} {len(f['data_dims'])} {dd[0]} {dd[1]} "
+            f"{e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]}"
+        )
+    L.append(f"scalars_size {plan['scalars_size']}")
+    L.append(f"nkernels {len(plan['kernels'])}")
+    for k in plan["kernels"]:
+        e = k["extent"]
+        kind = {"par": 0, "seq": 1, "stream": 2}[k["kind"]]
+        tile = k.get("tile", [k["block"][0], k["block"][1], 1])
+        L.append(
+            f"kernel {k['name']} {kind} {k['block'][0]} {k['block'][1]} {k['block'][2]} "
+            f"{tile[0]} {tile[1]} {tile[2]} {e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]} {b(k['k_lo'])} {b(k['k_hi'])} {k['smem']}"
+        )
+    L.append(f"nsteps {len(plan['steps'])}")
+    for s in plan["steps"]:
+        if s["t"] == "launch":
+            L.append(f"step launch {s['kernel']}")
+        else:
+            L.append(f"step levels {0 if s['order'] == 'forward' else 1} {len(s['sections'])}")
+            for sec in s["sections"]:
+                L.append(
+                    f"section {b(sec['interval'][0])} {b(sec['interval'][1])} {len(sec['kernels'])} "
+                    + " ".join(str(k) for k in sec["kernels"])
+                )
+    L.append("end")
+    return "\n".join(L) + "\n"

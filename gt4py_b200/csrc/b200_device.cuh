@@ -1,0 +1,158 @@
+// Device-side runtime of the b200 stencil backend: argument block shared by every generated kernel
+// and the arithmetic helpers that give GTScript native functions NumPy-ufunc semantics
+// (reference oracle arithmetic: src/gt4py/cartesian/gtc/ufuncs.py:15-93, gtc/common.py:910-993).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// One API field or backend-owned temporary, as seen by a kernel.
+//   p      : address of the element at the *origin* (domain point (0,0,0), data index 0)
+//   s[0..2]: element strides along I, J, K (0 when the field lacks the axis -> broadcast)
+//   s[3..4]: element strides of up to two data dimensions
+//   klo/khi: valid K index range relative to the origin (for clipping variable-K accesses,
+//            reference: cartesian/utils/field.py:54-58)
+struct FieldArg {
+  char* p;
+  long long s[5];
+  int klo, khi;
+};
+
+// Launch geometry common to all kernels of a stencil call.
+struct Geom {
+  int nI, nJ, nK;    // compute domain
+  int i_lo, i_hi;    // horizontal sub-box of the domain this launch covers (domain coordinates);
+  int j_lo, j_hi;    //   every stage additionally extends it by its own block extent
+  int k_lo, k_hi;    // K range override for level-by-level launches (k_lo < 0: use the section intervals)
+  int _pad;
+};
+
+template <class T>
+__device__ __forceinline__ T ld(const T* p) {
+  return *p;
+}
+template <class T>
+__device__ __forceinline__ T ldro(const T* p) {  // read-only path (field not written by this kernel)
+  return __ldg(p);
+}
+template <>
+__device__ __forceinline__ bool ldro<bool>(const bool* p) {
+  return __ldg(reinterpret_cast<const unsigned char*>(p)) != 0;
+}
+
+__device__ __forceinline__ int clampk(long long k, int lo, int hi) {
+  return (int)(k < lo ? lo : (k > hi - 1 ? hi - 1 : k));
+}
+
+// ---- NumPy-semantics helpers -------------------------------------------------------------------
+// np.minimum / np.maximum propagate NaN (fmin/fmax do not).
+__device__ __forceinline__ float min_(float a, float b) { return (isnan(a) || a < b) ? a : b; }
+__device__ __forceinline__ double min_(double a, double b) { return (isnan(a) || a < b) ? a : b; }
+__device__ __forceinline__ float max_(float a, float b) { return (isnan(a) || a > b) ? a : b; }
+__device__ __forceinline__ double max_(double a, double b) { return (isnan(a) || a > b) ? a : b; }
+template <class T>
+__device__ __forceinline__ T min_(T a, T b) { return a < b ? a : b; }
+template <class T>
+__device__ __forceinline__ T max_(T a, T b) { return a > b ? a : b; }
+
+__device__ __forceinline__ float abs_(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_(double a) { return fabs(a); }
+template <class T>
+__device__ __forceinline__ T abs_(T a) { return a < 0 ? (T)(-a) : a; }
+template <>
+__device__ __forceinline__ bool abs_<bool>(bool a) { return a; }
+
+// np.remainder: result has the sign of the divisor (Python %), unlike C fmod.
+__device__ __forceinline__ float mod_(float a, float b) {
+  float r = fmodf(a, b);
+  if (r != 0.0f && ((r < 0.0f) != (b < 0.0f))) r += b;
+  else if (r == 0.0f) r = copysignf(0.0f, b);
+  return r;
+}
+__device__ __forceinline__ double mod_(double a, double b) {
+  double r = fmod(a, b);
+  if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+  else if (r == 0.0) r = copysign(0.0, b);
+  return r;
+}
+template <class T>
+__device__ __forceinline__ T mod_(T a, T b) {
+  if (b == 0) return 0;
+  T r = a % b;
+  if (r != 0 && ((r < 0) != (b < 0))) r += b;
+  return r;
+}
+
+__device__ __forceinline__ float pow_(float a, float b) { return powf(a, b); }
+__device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+__device__ __forceinline__ double pow_(double a, float b) { return pow(a, (double)b); }
+__device__ __forceinline__ double pow_(float a, double b) { return pow((double)a, b); }
+template <class T, class U>
+__device__ __forceinline__ T pow_(T a, U b) {  // integer power (np.power on ints; negative exponent -> 0 here)
+  T r = 1;
+  long long e = (long long)b;
+  if (e < 0) return (a == 1) ? (T)1 : (T)0;
+  while (e) {
+    if (e & 1) r = (T)(r * a);
+    a = (T)(a * a);
+    e >>= 1;
+  }
+  return r;
+}
+__device__ __forceinline__ float pow_(float a, int b) { return powf(a, (float)b); }
+__device__ __forceinline__ float pow_(float a, long long b) { return powf(a, (float)b); }
+__device__ __forceinline__ double pow_(double a, int b) { return pow(a, (double)b); }
+__device__ __forceinline__ double pow_(double a, long long b) { return pow(a, (double)b); }
+
+// np.round == rint (half to even); round_away_from_zero = copysign(floor(|x| + 0.5), x)
+__device__ __forceinline__ float round_(float a) { return rintf(a); }
+__device__ __forceinline__ double round_(double a) { return rint(a); }
+__device__ __forceinline__ float round_away_(float a) { return copysignf(floorf(fabsf(a) + 0.5f), a); }
+__device__ __forceinline__ double round_away_(double a) { return copysign(floor(fabs(a) + 0.5), a); }
+
+#define B200_UNARY(NAME, F32FN, F64FN)                                        \
+  __device__ __forceinline__ float NAME(float a) { return F32FN(a); }         \
+  __device__ __forceinline__ double NAME(double a) { return F64FN(a); }
+B200_UNARY(sin_, sinf, sin)
+B200_UNARY(cos_, cosf, cos)
+B200_UNARY(tan_, tanf, tan)
+B200_UNARY(asin_, asinf, asin)
+B200_UNARY(acos_, acosf, acos)
+B200_UNARY(atan_, atanf, atan)
+B200_UNARY(sinh_, sinhf, sinh)
+B200_UNARY(cosh_, coshf, cosh)
+B200_UNARY(tanh_, tanhf, tanh)
+B200_UNARY(asinh_, asinhf, asinh)
+B200_UNARY(acosh_, acoshf, acosh)
+B200_UNARY(atanh_, atanhf, atanh)
+B200_UNARY(sqrt_, sqrtf, sqrt)
+B200_UNARY(exp_, expf, exp)
+B200_UNARY(log_, logf, log)
+B200_UNARY(log10_, log10f, log10)
+B200_UNARY(gamma_, tgammaf, tgamma)
+B200_UNARY(cbrt_, cbrtf, cbrt)
+B200_UNARY(floor_, floorf, floor)
+B200_UNARY(ceil_, ceilf, ceil)
+B200_UNARY(trunc_, truncf, trunc)
+B200_UNARY(erf_, erff, erf)
+B200_UNARY(erfc_, erfcf, erfc)
+#undef B200_UNARY
+// integer arguments of float-only functions behave like NumPy: promote to double
+template <class T> __device__ __forceinline__ double sqrt_(T a) { return sqrt((double)a); }
+template <class T> __device__ __forceinline__ T floor_(T a) { return a; }
+template <class T> __device__ __forceinline__ T ceil_(T a) { return a; }
+template <class T> __device__ __forceinline__ T trunc_(T a) { return a; }
+
+__device__ __forceinline__ bool isfinite_(float a) { return isfinite(a); }
+__device__ __forceinline__ bool isfinite_(double a) { return isfinite(a); }
+__device__ __forceinline__ bool isinf_(float a) { return isinf(a); }
+__device__ __forceinline__ bool isinf_(double a) { return isinf(a); }
+__device__ __forceinline__ bool isnan_(float a) { return isnan(a); }
+__device__ __forceinline__ bool isnan_(double a) { return isnan(a); }
+template <class T> __device__ __forceinline__ bool isfinite_(T) { return true; }
+template <class T> __device__ __forceinline__ bool isinf_(T) { return false; }
+template <class T> __device__ __forceinline__ bool isnan_(T) { return false; }
+
+}  // namespace b200

@@ -1,0 +1,587 @@
+// libgt4py_b200.so — the thin C-ABI launcher of the b200 stencil backend (see include/gt4py_b200.h).
+//
+// Stands in for the per-stencil pybind11 extension + gridtools::stencil::run of the reference
+// (backend/gtc_common.py:65-103, gtc/gtcpp/gtcpp_codegen.py:267-285): loads the sm_100a cubin the
+// b200 code generator produced, owns the scratch for surviving temporaries (GT_DECLARE_TMP in the
+// reference, gtcpp_codegen.py:241-247), builds the kernel argument block from borrowed device
+// pointers and enqueues the kernels of the launch plan on the caller's stream.
+//
+// Only the CUDA runtime is linked (statically); NCCL is resolved with dlopen at first use so the
+// library loads on machines without NCCL/driver and fails loudly, never silently, when used there.
+#include "../../include/gt4py_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? B200_ERR_NO_DEVICE \
+                                                                                : B200_ERR_CUDA,   \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+  } while (0)
+
+// ---- mirror of the device-side argument block (csrc/b200_device.cuh) -----------------------------
+struct FieldArg {
+  char* p;
+  long long s[5];
+  int klo, khi;
+};
+struct Geom {
+  int nI, nJ, nK;
+  int i_lo, i_hi, j_lo, j_hi;
+  int k_lo, k_hi;
+  int _pad;
+};
+static_assert(sizeof(FieldArg) == 56, "FieldArg layout");
+static_assert(sizeof(Geom) == 40, "Geom layout");
+
+struct Bound {
+  int level;  // 0 = START, 1 = END
+  int off;
+  int resolve(int nK) const { return level == 0 ? off : nK + off; }
+};
+
+struct FieldPlan {
+  std::string name;
+  int is_temp, itemsize, dims[3], ndata, data[2];
+  int ei0, ei1, ej0, ej1;
+};
+struct KernelPlan {
+  std::string name;
+  int kind;  // 0 par, 1 seq, 2 stream
+  int block[3], tile[3];
+  int ei0, ei1, ej0, ej1;
+  Bound k_lo, k_hi;
+  int smem;
+  cudaKernel_t fn = nullptr;
+};
+struct SectionPlan {
+  Bound k0, k1;
+  std::vector<int> kernels;
+};
+struct StepPlan {
+  int type;  // 0 launch, 1 levels
+  int kernel = -1;
+  int order = 0;  // 0 forward, 1 backward
+  std::vector<SectionPlan> sections;
+};
+
+}  // namespace
+
+struct b200_stencil {
+  std::string name;
+  std::vector<FieldPlan> fields;
+  int n_api = 0;
+  size_t scalars_size = 0;
+  std::vector<KernelPlan> kernels;
+  std::vector<StepPlan> steps;
+  cudaLibrary_t lib = nullptr;
+  std::vector<char> image;
+  // scratch for temporaries (grow-only, keyed by the domain of the last call)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int device = -1;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int parse_plan(const char* text, b200_stencil* st) {
+  std::istringstream in(text);
+  std::string tok;
+  int version = 0;
+  if (!(in >> tok >> version) || tok != "b200plan" || version != 1)
+    return fail(B200_ERR_INVALID, "launch plan: bad header");
+  int nfields = 0, nkernels = 0, nsteps = 0;
+  while (in >> tok) {
+    if (tok == "name") {
+      in >> st->name;
+    } else if (tok == "nfields") {
+      in >> nfields;
+    } else if (tok == "field") {
+      FieldPlan f;
+      in >> f.name >> f.is_temp >> f.itemsize >> f.dims[0] >> f.dims[1] >> f.dims[2] >> f.ndata >> f.data[0] >>
+          f.data[1] >> f.ei0 >> f.ei1 >> f.ej0 >> f.ej1;
+      st->fields.push_back(f);
+    } else if (tok == "scalars_size") {
+      in >> st->scalars_size;
+    } else if (tok == "nkernels") {
+      in >> nkernels;
+    } else if (tok == "kernel") {
+      KernelPlan k;
+      in >> k.name >> k.kind >> k.block[0] >> k.block[1] >> k.block[2] >> k.tile[0] >> k.tile[1] >> k.tile[2] >>
+          k.ei0 >> k.ei1 >> k.ej0 >> k.ej1 >> k.k_lo.level >> k.k_lo.off >> k.k_hi.level >> k.k_hi.off >> k.smem;
+      st->kernels.push_back(k);
+    } else if (tok == "nsteps") {
+      in >> nsteps;
+    } else if (tok == "step") {
+      std::string kind;
+      in >> kind;
+      StepPlan s;
+      if (kind == "launch") {
+        s.type = 0;
+        in >> s.kernel;
+      } else if (kind == "levels") {
+        s.type = 1;
+        int nsec = 0;
+        in >> s.order >> nsec;
+        for (int i = 0; i < nsec; ++i) {
+          std::string t2;
+          SectionPlan sec;
+          int nk = 0;
+          in >> t2 >> sec.k0.level >> sec.k0.off >> sec.k1.level >> sec.k1.off >> nk;
+          if (t2 != "section") return fail(B200_ERR_INVALID, "launch plan: expected 'section'");
+          sec.kernels.resize(nk);
+          for (int j = 0; j < nk; ++j) in >> sec.kernels[j];
+          s.sections.push_back(sec);
+        }
+      } else {
+        return fail(B200_ERR_INVALID, "launch plan: unknown step '%s'", kind.c_str());
+      }
+      st->steps.push_back(s);
+    } else if (tok == "end") {
+      break;
+    } else {
+      return fail(B200_ERR_INVALID, "launch plan: unknown token '%s'", tok.c_str());
+    }
+  }
+  if (!in || (int)st->fields.size() != nfields || (int)st->kernels.size() != nkernels ||
+      (int)st->steps.size() != nsteps)
+    return fail(B200_ERR_INVALID, "launch plan: truncated or inconsistent");
+  for (auto& f : st->fields)
+    if (!f.is_temp) st->n_api++;
+  for (auto& s : st->steps) {
+    if (s.type == 0 && (s.kernel < 0 || s.kernel >= nkernels)) return fail(B200_ERR_INVALID, "plan: kernel index");
+    for (auto& sec : s.sections)
+      for (int k : sec.kernels)
+        if (k < 0 || k >= nkernels) return fail(B200_ERR_INVALID, "plan: kernel index");
+  }
+  return B200_OK;
+}
+
+// Temporaries: I stride-1, padded to 32 elements so that the origin column is 128-byte aligned.
+struct TempLayout {
+  size_t offset, bytes;
+  long long s[5];
+  int origin[3], shape[3];
+};
+
+TempLayout temp_layout(const FieldPlan& f, const int32_t dom[3], size_t offset) {
+  TempLayout t{};
+  int ni = f.dims[0] ? dom[0] + (f.ei1 - f.ei0) : 1;
+  int nj = f.dims[1] ? dom[1] + (f.ej1 - f.ej0) : 1;
+  int nk = f.dims[2] ? dom[2] : 1;
+  int lead = f.dims[0] ? (int)align_up((size_t)(-f.ei0), 32) : 0;  // pad so that origin is aligned
+  long long pitch_i = f.dims[0] ? (long long)align_up((size_t)(lead + dom[0] + f.ei1), 32) : 1;
+  long long nd = 1;
+  for (int d = 0; d < f.ndata; ++d) nd *= f.data[d];
+  // layout (fastest to slowest): I, J, K, data0, data1
+  t.s[0] = f.dims[0] ? 1 : 0;
+  t.s[1] = f.dims[1] ? pitch_i : 0;
+  t.s[2] = f.dims[2] ? pitch_i * nj : 0;
+  long long vol = pitch_i * nj * nk;
+  t.s[3] = f.ndata > 0 ? vol * (f.ndata > 1 ? f.data[1] : 1) : 0;
+  t.s[4] = f.ndata > 1 ? vol : 0;
+  t.origin[0] = f.dims[0] ? lead : 0;
+  t.origin[1] = f.dims[1] ? -f.ej0 : 0;
+  t.origin[2] = 0;
+  t.shape[0] = ni;
+  t.shape[1] = nj;
+  t.shape[2] = nk;
+  t.offset = offset;
+  t.bytes = align_up((size_t)(vol * nd) * f.itemsize, 256);
+  return t;
+}
+
+int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, int k_hi, cudaStream_t stream) {
+  Geom* g = reinterpret_cast<Geom*>(blob.data());
+  int nx = (g->i_hi + k.ei1) - (g->i_lo + k.ei0);
+  int ny = (g->j_hi + k.ej1) - (g->j_lo + k.ej0);
+  int nz = k.kind == 1 ? 1 : (k_hi - k_lo);
+  if (nx <= 0 || ny <= 0 || nz <= 0) return 0;
+  g->k_lo = k_lo;
+  g->k_hi = k_hi;
+  dim3 grid((nx + k.tile[0] - 1) / k.tile[0], (ny + k.tile[1] - 1) / k.tile[1], (nz + k.tile[2] - 1) / k.tile[2]);
+  dim3 block(k.block[0], k.block[1], k.block[2]);
+  if (grid.y > 65535 || grid.z > 65535) return fail(B200_ERR_INVALID, "grid too large for kernel %s", k.name.c_str());
+  void* params[1] = {blob.data()};
+  CU(cudaLaunchKernel((const void*)k.fn, grid, block, params, (size_t)k.smem, stream));
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+
+int b200_device_info(int device, int* n_devices, int* sm_major, int* sm_minor, int* n_sms) {
+  int n = 0;
+  CU(cudaGetDeviceCount(&n));
+  if (n_devices) *n_devices = n;
+  if (device >= n) return fail(B200_ERR_NO_DEVICE, "device %d of %d", device, n);
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  if (sm_major) *sm_major = p.major;
+  if (sm_minor) *sm_minor = p.minor;
+  if (n_sms) *n_sms = p.multiProcessorCount;
+  return B200_OK;
+}
+
+int b200_stencil_load(const void* image, size_t image_size, const char* plan_text, b200_stencil_t** out) {
+  if (!image || !image_size || !plan_text || !out) return fail(B200_ERR_INVALID, "b200_stencil_load: null argument");
+  b200_stencil* st = new b200_stencil();
+  int rc = parse_plan(plan_text, st);
+  if (rc != B200_OK) {
+    delete st;
+    return rc;
+  }
+  st->image.assign((const char*)image, (const char*)image + image_size);
+  cudaError_t e = cudaGetDevice(&st->device);
+  if (e == cudaSuccess) e = cudaFree(0);  // make sure the primary context exists
+  if (e == cudaSuccess)
+    e = cudaLibraryLoadData(&st->lib, st->image.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) {
+    delete st;
+    return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? B200_ERR_NO_DEVICE : B200_ERR_CUDA,
+                "loading stencil image failed: %s", cudaGetErrorString(e));
+  }
+  for (auto& k : st->kernels) {
+    e = cudaLibraryGetKernel(&k.fn, st->lib, k.name.c_str());
+    if (e == cudaSuccess && k.smem > 48 * 1024)
+      e = cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem);
+    if (e != cudaSuccess) {
+      std::string kn = k.name;
+      cudaLibraryUnload(st->lib);
+      delete st;
+      return fail(B200_ERR_CUDA, "kernel %s: %s", kn.c_str(), cudaGetErrorString(e));
+    }
+  }
+  *out = st;
+  return B200_OK;
+}
+
+int b200_stencil_unload(b200_stencil_t* st) {
+  if (!st) return B200_OK;
+  if (st->scratch) cudaFree(st->scratch);
+  if (st->lib) cudaLibraryUnload(st->lib);
+  delete st;
+  return B200_OK;
+}
+
+int b200_stencil_num_fields(const b200_stencil_t* st) { return st ? st->n_api : B200_ERR_INVALID; }
+size_t b200_stencil_scalars_size(const b200_stencil_t* st) { return st ? st->scalars_size : 0; }
+int b200_stencil_num_kernels(const b200_stencil_t* st) { return st ? (int)st->kernels.size() : B200_ERR_INVALID; }
+const char* b200_stencil_kernel_name(const b200_stencil_t* st, int index) {
+  if (!st || index < 0 || index >= (int)st->kernels.size()) return nullptr;
+  return st->kernels[index].name.c_str();
+}
+
+int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
+                     size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], void* stream_) {
+  if (!st || !domain) return fail(B200_ERR_INVALID, "b200_stencil_run: null argument");
+  if (nfields != st->n_api)
+    return fail(B200_ERR_INVALID, "stencil %s expects %d fields, got %d", st->name.c_str(), st->n_api, nfields);
+  if (scalars_size != st->scalars_size || (scalars_size && !scalars))
+    return fail(B200_ERR_INVALID, "stencil %s expects %zu bytes of scalars, got %zu", st->name.c_str(),
+                st->scalars_size, scalars_size);
+  if (domain[0] <= 0 || domain[1] <= 0 || domain[2] <= 0)
+    return fail(B200_ERR_INVALID, "empty compute domain (%d, %d, %d)", domain[0], domain[1], domain[2]);
+  cudaStream_t stream = (cudaStream_t)stream_;
+
+  // -- scratch for temporaries ---------------------------------------------------------------
+  const size_t nf = st->fields.size();
+  std::vector<TempLayout> tl(nf);
+  size_t need = 0;
+  for (size_t n = 0; n < nf; ++n)
+    if (st->fields[n].is_temp) {
+      tl[n] = temp_layout(st->fields[n], domain, need);
+      need += tl[n].bytes;
+    }
+  if (need > st->scratch_bytes) {
+    if (st->scratch) {
+      CU(cudaStreamSynchronize(stream));
+      CU(cudaFree(st->scratch));
+      st->scratch = nullptr;
+      st->scratch_bytes = 0;
+    }
+    CU(cudaMalloc(&st->scratch, need));
+    st->scratch_bytes = need;
+  }
+
+  // -- argument block --------------------------------------------------------------------------
+  const size_t nslots = nf ? nf : 1;
+  const size_t scal_off = sizeof(Geom) + sizeof(FieldArg) * nslots;
+  std::vector<char> blob(align_up(scal_off + st->scalars_size, 8), 0);
+  Geom* g = reinterpret_cast<Geom*>(blob.data());
+  g->nI = domain[0];
+  g->nJ = domain[1];
+  g->nK = domain[2];
+  g->i_lo = subbox ? subbox[0] : 0;
+  g->i_hi = subbox ? subbox[1] : domain[0];
+  g->j_lo = subbox ? subbox[2] : 0;
+  g->j_hi = subbox ? subbox[3] : domain[1];
+  FieldArg* fa = reinterpret_cast<FieldArg*>(blob.data() + sizeof(Geom));
+  int api = 0;
+  for (size_t n = 0; n < nf; ++n) {
+    const FieldPlan& fp = st->fields[n];
+    FieldArg& a = fa[n];
+    if (fp.is_temp) {
+      const TempLayout& t = tl[n];
+      for (int d = 0; d < 5; ++d) a.s[d] = t.s[d];
+      long long off = (long long)t.origin[0] * t.s[0] + (long long)t.origin[1] * t.s[1];
+      a.p = (char*)st->scratch + t.offset + off * fp.itemsize;
+      a.klo = 0;
+      a.khi = t.shape[2];
+    } else {
+      const b200_field_t& f = fields[api++];
+      if (!f.data) {  // unreferenced argument (AccessKind.NONE)
+        a.p = nullptr;
+        continue;
+      }
+      long long off = 0;
+      for (int d = 0; d < 5; ++d) a.s[d] = f.strides[d];
+      for (int d = 0; d < 3; ++d)
+        if (fp.dims[d]) off += (long long)f.origin[d] * f.strides[d];
+      a.p = (char*)f.data + off * fp.itemsize;
+      a.klo = fp.dims[2] ? -f.origin[2] : 0;
+      a.khi = fp.dims[2] ? f.shape[2] - f.origin[2] : 1;
+    }
+  }
+  if (st->scalars_size) memcpy(blob.data() + scal_off, scalars, st->scalars_size);
+
+  // -- steps -------------------------------------------------------------------------------------
+  int launches = 0;
+  const int nK = domain[2];
+  for (auto& s : st->steps) {
+    if (s.type == 0) {
+      KernelPlan& k = st->kernels[s.kernel];
+      int rc = launch(st, k, blob, k.k_lo.resolve(nK), k.k_hi.resolve(nK), stream);
+      if (rc < 0) return rc;
+      launches += rc;
+    } else {
+      // level-by-level: sections are listed in execution order
+      for (auto& sec : s.sections) {
+        int k0 = sec.k0.resolve(nK), k1 = sec.k1.resolve(nK);
+        for (int kk = 0; kk < k1 - k0; ++kk) {
+          int level = s.order == 0 ? k0 + kk : k1 - 1 - kk;
+          for (int ki : sec.kernels) {
+            int rc = launch(st, st->kernels[ki], blob, level, level + 1, stream);
+            if (rc < 0) return rc;
+            launches += rc;
+          }
+        }
+      }
+    }
+  }
+  return launches;
+}
+
+// ---- streams / events --------------------------------------------------------------------------
+int b200_stream_create(void** stream) {
+  cudaStream_t s;
+  CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = s;
+  return B200_OK;
+}
+int b200_stream_destroy(void* stream) {
+  CU(cudaStreamDestroy((cudaStream_t)stream));
+  return B200_OK;
+}
+int b200_stream_synchronize(void* stream) {
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return B200_OK;
+}
+int b200_event_create(void** event) {
+  cudaEvent_t e;
+  CU(cudaEventCreate(&e));
+  *event = e;
+  return B200_OK;
+}
+int b200_event_destroy(void* event) {
+  CU(cudaEventDestroy((cudaEvent_t)event));
+  return B200_OK;
+}
+int b200_event_record(void* event, void* stream) {
+  CU(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return B200_OK;
+}
+int b200_stream_wait_event(void* stream, void* event) {
+  CU(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+  return B200_OK;
+}
+int b200_event_elapsed_ms(void* start, void* stop, float* ms) {
+  CU(cudaEventSynchronize((cudaEvent_t)stop));
+  CU(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return B200_OK;
+}
+
+// ---- strided slab copy -----------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+// One 16-byte (or 4-byte tail-safe) lane per thread along the row, rows on blockIdx.y.
+__global__ void pack2d_kernel(char* __restrict__ dst, size_t dst_pitch, const char* __restrict__ src, size_t src_pitch,
+                              size_t row_bytes, size_t rows) {
+  size_t row = blockIdx.y;
+  size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  for (; row < rows; row += gridDim.y) {
+    const char* s = src + row * src_pitch;
+    char* d = dst + row * dst_pitch;
+    if (x + 16 <= row_bytes && ((((size_t)s | (size_t)d) + x) & 15) == 0 && ((src_pitch | dst_pitch) & 15) == 0) {
+      *reinterpret_cast<int4*>(d + x) = *reinterpret_cast<const int4*>(s + x);
+    } else {
+      for (size_t b = x; b < row_bytes && b < x + 16; ++b) d[b] = s[b];
+    }
+  }
+}
+
+// ---- NCCL through dlopen -------------------------------------------------------------------------
+struct Id128 {
+  char internal[B200_NCCL_UNIQUE_ID_BYTES];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+  if (g_nccl.handle) return B200_OK;
+  const char* names[] = {getenv("B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(B200_ERR_NCCL, "cannot load NCCL: %s", dlerror());
+#define SYM(field, name)                                                        \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                    \
+  if (!g_nccl.field) return fail(B200_ERR_NCCL, "NCCL symbol %s missing", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.handle = h;
+  return B200_OK;
+}
+
+#define NC(call)                                                                                  \
+  do {                                                                                            \
+    int r_ = (call);                                                                              \
+    if (r_ != 0) return fail(B200_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));   \
+  } while (0)
+
+}  // namespace
+
+struct b200_comm {
+  void* comm = nullptr;
+  int n_ranks = 0, rank = 0;
+};
+
+extern "C" {
+
+int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows,
+                 void* stream) {
+  if (!rows || !row_bytes) return B200_OK;
+  dim3 block(128);
+  dim3 grid((unsigned)((row_bytes + 16 * 128 - 1) / (16 * 128)), (unsigned)(rows < 65535 ? rows : 65535));
+  pack2d_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((char*)dst, dst_pitch, (const char*)src, src_pitch,
+                                                          row_bytes, rows);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_comm_unique_id(void* id_out) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  NC(g_nccl.GetUniqueId(id_out));
+  return B200_OK;
+}
+
+int b200_comm_init(b200_comm_t** out, const void* unique_id, int n_ranks, int rank) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  Id128 id;
+  memcpy(&id, unique_id, sizeof id);
+  b200_comm* c = new b200_comm();
+  c->n_ranks = n_ranks;
+  c->rank = rank;
+  int r = g_nccl.CommInitRank(&c->comm, n_ranks, id, rank);
+  if (r != 0) {
+    delete c;
+    return fail(B200_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+  }
+  *out = c;
+  return B200_OK;
+}
+
+int b200_comm_destroy(b200_comm_t* comm) {
+  if (!comm) return B200_OK;
+  if (comm->comm) g_nccl.CommDestroy(comm->comm);
+  delete comm;
+  return B200_OK;
+}
+
+int b200_halo_exchange(b200_comm_t* comm, const b200_halo_t* halos, int n_halos, int peer_lo, int peer_hi,
+                       void* stream_) {
+  if (!comm || (!halos && n_halos)) return fail(B200_ERR_INVALID, "b200_halo_exchange: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int ncclChar = 0;
+  NC(g_nccl.GroupStart());
+  for (int n = 0; n < n_halos; ++n) {
+    const b200_halo_t& h = halos[n];
+    if (peer_lo >= 0) {
+      NC(g_nccl.Send(h.send_lo, h.bytes, ncclChar, peer_lo, comm->comm, stream));
+      NC(g_nccl.Recv(h.recv_lo, h.bytes, ncclChar, peer_lo, comm->comm, stream));
+    }
+    if (peer_hi >= 0) {
+      NC(g_nccl.Send(h.send_hi, h.bytes, ncclChar, peer_hi, comm->comm, stream));
+      NC(g_nccl.Recv(h.recv_hi, h.bytes, ncclChar, peer_hi, comm->comm, stream));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+"""JIT driver: CUDA source -> sm_100a cubin with nvcc, cached on disk.
+
+Replaces the reference's setuptools/pybind11/nvcc extension build (reference:
+backend/pyext_builder.py:53-167, 324-359; flag conventions utils/compiler.py:154-189): generated
+kernels are plain SIMT C++ without template libraries, so a stencil compiles in ~1-2 s to a bare
+cubin that the launcher loads through cudaLibraryLoadData.
+
+FMA contraction is OFF by default (``-fmad=false``): the NumPy oracle never fuses, the flux limiter
+of horizontal diffusion is discontinuous in the sign of a product (SURVEY §7 hard parts), and the
+kernels are HBM-bound so the extra instruction is free.  IEEE division / sqrt, no fast-math.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import pathlib
+import shutil
+import subprocess
+import tempfile
+from typing import Dict, Optional, Sequence
+
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
+
+
+def cache_dir() -> pathlib.Path:
+    root = os.environ.get("GT4PY_B200_CACHE")
+    path = pathlib.Path(root) if root else pathlib.Path(__file__).resolve().parent / "_cache"
+    path.mkdir(parents=True, exist_ok=True)
+    return path
+
+
+def nvcc_path() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("b200: nvcc not found (set NVCC or CUDA_HOME); no CPU fallback exists")
+    return cand
+
+
+def compile_flags(options: Optional[Dict] = None) -> list:
+    options = options or {}
+    flags = list(ARCH_FLAGS) + ["-std=c++17", "-lineinfo", f"-O{int(options.get('opt_level', 3))}"]
+    flags.append("-fmad=true" if options.get("fmad", False) else "-fmad=false")
+    if options.get("debug_mode", False):
+        flags += ["-G"]
+    flags += list(options.get("extra_opt_flags", []) or [])
+    return flags
+
+
+def compile_cubin(source: str, options: Optional[Dict] = None, *, name: str = "stencil", verbose: bool = False) -> bytes:
+    """Compile `source` to a cubin (cached by content hash of source + flags + device header)."""
+    flags = compile_flags(options)
+    header = (CSRC / "b200_device.cuh").read_bytes()
+    key = hashlib.sha256(source.encode() + b"\0" + " ".join(flags).encode() + b"\0" + header).hexdigest()[:24]
+    cdir = cache_dir()
+    cubin = cdir / f"{name}_{key}.cubin"
+    if cubin.exists() and cubin.stat().st_size > 0:
+        return cubin.read_bytes()
+    cu = cdir / f"{name}_{key}.cu"
+    cu.write_text(source, encoding="utf-8")
+    with tempfile.NamedTemporaryFile(dir=cdir, suffix=".cubin", delete=False) as tmp:
+        tmp_path = tmp.name
+    cmd = [nvcc_path(), *flags, "-cubin", "-I", str(CSRC), str(cu), "-o", tmp_path]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        try:
+            os.unlink(tmp_path)
+        except OSError:
+            pass
+        raise RuntimeError(f"b200: nvcc failed for {name}:\n{proc.stderr[-4000:]}\n(source kept at {cu})")
+    if verbose and proc.stderr:
+        print(proc.stderr)
+    os.replace(tmp_path, cubin)
+    return cubin.read_bytes()
+
+
+def cubin_path(source: str, options: Optional[Dict] = None, *, name: str = "stencil") -> pathlib.Path:
+    flags = compile_flags(options)
+    header = (CSRC / "b200_device.cuh").read_bytes()
+    key = hashlib.sha256(source.encode() + b"\0" + " ".join(flags).encode() + b"\0" + header).hexdigest()[:24]
+    return cache_dir() / f"{name}_{key}.cubin"
+
+
+def build_launcher(force: bool = False) -> pathlib.Path:
+    """Build libgt4py_b200.so in-tree (nvcc -shared, sm_100a)."""
+    out = CSRC.parent / "libgt4py_b200.so"
+    srcs = [CSRC / "launcher.cu"]
+    deps = srcs + [CSRC.parent.parent / "include" / "gt4py_b200.h"]
+    if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
+    cmd = [
+        nvcc_path(), *ARCH_FLAGS, "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+        "-cudart", "static", *[str(s) for s in srcs], "-o", str(out), "-ldl",
+    ]  # fmt: skip
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"b200: building the launcher failed:\n{proc.stderr[-4000:]}")
+    return out

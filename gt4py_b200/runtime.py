@@ -1,0 +1,301 @@
+"""Python side of the C-ABI: ctypes binding of libgt4py_b200.so and the compiled-stencil object.
+
+This is the `run()` half of the reference's generated module (reference:
+backend/templates/stencil_module.py.in:160-169 -> backend/gtc_common.py:144-168
+`pyext_module.run_computation(domain, field, origin, …, scalars…, exec_info)`): it turns the
+already-normalised (arrays, origins, domain, scalars) of one stencil call into the plain-C structs
+of include/gt4py_b200.h and enqueues the kernels.  There is no CPU path: without the shared library
+or without a CUDA device every entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import pathlib
+import struct
+import threading
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import codegen, ir as b2ir, jit
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libgt4py_b200.so"
+
+EXPORTED_SYMBOLS = (
+    "b200_abi_version", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
+    "b200_stencil_num_fields", "b200_stencil_scalars_size", "b200_stencil_num_kernels", "b200_stencil_kernel_name",
+    "b200_stencil_run", "b200_stream_create", "b200_stream_destroy", "b200_stream_synchronize",
+    "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
+    "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
+    "b200_halo_exchange", "b200_pack_2d",
+)  # fmt: skip
+
+
+class B200Field(ctypes.Structure):
+    _fields_ = [
+        ("data", ctypes.c_void_p),
+        ("strides", ctypes.c_int64 * 5),
+        ("origin", ctypes.c_int32 * 3),
+        ("shape", ctypes.c_int32 * 3),
+    ]
+
+
+class B200Halo(ctypes.Structure):
+    _fields_ = [
+        ("send_lo", ctypes.c_void_p),
+        ("recv_lo", ctypes.c_void_p),
+        ("send_hi", ctypes.c_void_p),
+        ("recv_hi", ctypes.c_void_p),
+        ("bytes", ctypes.c_size_t),
+    ]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen libgt4py_b200.so (building it in-tree first if it is missing and nvcc exists)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            if not build_if_missing:
+                raise B200Error(f"b200: {LIB_PATH} is missing (run __graft_entry__.build())")
+            jit.build_launcher()
+        lib = ctypes.CDLL(str(LIB_PATH))
+        vp, ci, cz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+        pvp = ctypes.POINTER(ctypes.c_void_p)
+        pi = ctypes.POINTER(ctypes.c_int)
+        sig = {
+            "b200_abi_version": (ci, []),
+            "b200_last_error": (ctypes.c_char_p, []),
+            "b200_device_info": (ci, [ci, pi, pi, pi, pi]),
+            "b200_stencil_load": (ci, [vp, cz, ctypes.c_char_p, pvp]),
+            "b200_stencil_unload": (ci, [vp]),
+            "b200_stencil_num_fields": (ci, [vp]),
+            "b200_stencil_scalars_size": (cz, [vp]),
+            "b200_stencil_num_kernels": (ci, [vp]),
+            "b200_stencil_kernel_name": (ctypes.c_char_p, [vp, ci]),
+            "b200_stencil_run": (ci, [vp, ctypes.POINTER(B200Field), ci, vp, cz, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp]),
+            "b200_stream_create": (ci, [pvp]),
+            "b200_stream_destroy": (ci, [vp]),
+            "b200_stream_synchronize": (ci, [vp]),
+            "b200_event_create": (ci, [pvp]),
+            "b200_event_destroy": (ci, [vp]),
+            "b200_event_record": (ci, [vp, vp]),
+            "b200_stream_wait_event": (ci, [vp, vp]),
+            "b200_event_elapsed_ms": (ci, [vp, vp, ctypes.POINTER(ctypes.c_float)]),
+            "b200_comm_unique_id": (ci, [vp]),
+            "b200_comm_init": (ci, [pvp, vp, ci, ci]),
+            "b200_comm_destroy": (ci, [vp]),
+            "b200_halo_exchange": (ci, [vp, ctypes.POINTER(B200Halo), ci, ci, ci, vp]),
+            "b200_pack_2d": (ci, [vp, cz, vp, cz, cz, cz, vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.b200_abi_version() != 1:
+            raise B200Error("b200: ABI version mismatch between gt4py_b200 and libgt4py_b200.so")
+        _lib = lib
+        return lib
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = load_library().b200_last_error().decode(errors="replace")
+        raise B200Error(f"b200 launcher error {rc}: {msg}")
+    return rc
+
+
+def device_info(device: int = 0) -> Dict[str, int]:
+    lib = load_library()
+    n, ma, mi, sms = (ctypes.c_int(0) for _ in range(4))
+    check(lib.b200_device_info(device, ctypes.byref(n), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(sms)))
+    return {"n_devices": n.value, "sm_major": ma.value, "sm_minor": mi.value, "n_sms": sms.value}
+
+
+# ---- array views ------------------------------------------------------------------------------------
+class ArrayView:
+    """(pointer, shape, element strides, dtype) of a device array, whatever object it came from."""
+
+    __slots__ = ("ptr", "shape", "strides", "dtype", "obj")
+
+    def __init__(self, ptr, shape, strides, dtype, obj=None):
+        self.ptr = int(ptr)
+        self.shape = tuple(int(s) for s in shape)
+        self.strides = tuple(int(s) for s in strides)
+        self.dtype = np.dtype(dtype)
+        self.obj = obj
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def transpose(self, axes):
+        return ArrayView(self.ptr, [self.shape[a] for a in axes], [self.strides[a] for a in axes], self.dtype, self.obj)
+
+
+_TORCH_TO_NP = None
+
+
+def as_view(obj) -> ArrayView:
+    """Device array-like -> ArrayView.  Accepts DeviceArray, torch CUDA tensors and anything that
+    exports __cuda_array_interface__ (cupy, numba, …).  Host arrays are rejected: the reference
+    also refuses CPU arrays for GPU backends (storage/cartesian/utils.py:176-215)."""
+    global _TORCH_TO_NP
+    from .storage import DeviceArray
+
+    if isinstance(obj, ArrayView):
+        return obj
+    if isinstance(obj, DeviceArray):
+        return ArrayView(obj.data_ptr, obj.shape, obj.element_strides, obj.dtype, obj)
+    mod = type(obj).__module__
+    if mod.startswith("torch"):
+        import torch
+
+        if _TORCH_TO_NP is None:
+            _TORCH_TO_NP = {
+                torch.bool: np.dtype("bool"), torch.int8: np.dtype("int8"), torch.int16: np.dtype("int16"),
+                torch.int32: np.dtype("int32"), torch.int64: np.dtype("int64"), torch.float32: np.dtype("float32"),
+                torch.float64: np.dtype("float64"),
+            }  # fmt: skip
+        if not obj.is_cuda:
+            raise TypeError("b200: torch tensor arguments must live on a CUDA device")
+        return ArrayView(obj.data_ptr(), obj.shape, obj.stride(), _TORCH_TO_NP[obj.dtype], obj)
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        dtype = np.dtype(cai["typestr"])
+        shape = tuple(cai["shape"])
+        strides = cai.get("strides")
+        if strides is None:
+            acc, es = 1, []
+            for s in reversed(shape):
+                es.append(acc)
+                acc *= s
+            estrides = tuple(reversed(es))
+        else:
+            if any(s % dtype.itemsize for s in strides):
+                raise ValueError("b200: strides must be multiples of the item size")
+            estrides = tuple(s // dtype.itemsize for s in strides)
+        return ArrayView(cai["data"][0], shape, estrides, dtype, obj)
+    raise TypeError(f"b200: cannot use {type(obj)} as a device field (need a CUDA array)")
+
+
+def current_stream_handle() -> int:
+    import torch
+
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- compiled stencil -----------------------------------------------------------------------------
+class CompiledStencil:
+    """Generated CUDA code + launch plan of one stencil, loaded lazily into the launcher."""
+
+    def __init__(self, stencil_ir: Dict[str, Any], options: Optional[Dict[str, Any]] = None, *, name: Optional[str] = None):
+        self.ir = stencil_ir
+        self.options = dict(options or {})
+        self.name = name or stencil_ir["name"]
+        self.source, self.plan = codegen.generate(stencil_ir, self.options)
+        self.plan_text = codegen.plan_to_text(self.plan)
+        self.cubin = jit.compile_cubin(self.source, self.options, name=codegen._cname(self.name), verbose=bool(self.options.get("verbose")))
+        self._handle = None
+        self._api = [f for f in self.plan["fields"] if f["kind"] == "api"]
+        self._scalars = self.plan["scalars"]
+        self._scal_struct = self._make_scalar_packer()
+        self.last_launches = 0
+
+    def _make_scalar_packer(self):
+        fmt_of = {"bool": "?", "int8": "b", "int16": "h", "int32": "i", "int64": "q", "float32": "f", "float64": "d"}
+        fmt, pos = "<", 0
+        for s in self._scalars:
+            if s["offset"] > pos:
+                fmt += f"{s['offset'] - pos}x"
+            fmt += fmt_of[s["dtype"]]
+            pos = s["offset"] + b2ir.ITEMSIZE[s["dtype"]]
+        if self.plan["scalars_size"] > pos:
+            fmt += f"{self.plan['scalars_size'] - pos}x"
+        return struct.Struct(fmt)
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            lib = load_library()
+            h = ctypes.c_void_p()
+            buf = ctypes.create_string_buffer(self.cubin, len(self.cubin))
+            check(lib.b200_stencil_load(buf, len(self.cubin), self.plan_text.encode(), ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def kernel_names(self):
+        return [k["name"] for k in self.plan["kernels"]]
+
+    def pack_scalars(self, params: Dict[str, Any]) -> bytes:
+        vals = []
+        for s in self._scalars:
+            v = params.get(s["name"])
+            if v is None:
+                v = 0
+            vals.append(bool(v) if s["dtype"] == "bool" else (int(v) if s["dtype"].startswith("int") else float(v)))
+        return self._scal_struct.pack(*vals)
+
+    def make_field_descs(self, views: Dict[str, Optional[ArrayView]], origins: Dict[str, Sequence[int]]):
+        arr = (B200Field * max(1, len(self._api)))()
+        for n, f in enumerate(self._api):
+            v = views.get(f["name"])
+            d = arr[n]
+            if v is None:
+                d.data = None
+                continue
+            org = origins[f["name"]]
+            d.data = v.ptr
+            ax = 0
+            for a in range(3):
+                if f["dims"][a]:
+                    d.strides[a] = v.strides[ax]
+                    d.origin[a] = int(org[ax])
+                    d.shape[a] = v.shape[ax]
+                    ax += 1
+                else:
+                    d.strides[a] = 0
+                    d.origin[a] = 0
+                    d.shape[a] = 1
+            for dd in range(len(f["data_dims"])):
+                d.strides[3 + dd] = v.strides[ax + dd]
+        return arr
+
+    def run(self, fields: Dict[str, Any], params: Dict[str, Any], domain: Sequence[int], origins: Dict[str, Sequence[int]],
+            *, stream: Optional[int] = None, subbox: Optional[Sequence[int]] = None) -> int:
+        """Enqueue one stencil application; returns the number of kernel launches."""
+        views = {n: (as_view(a) if a is not None else None) for n, a in fields.items()}
+        return self.run_views(views, self.pack_scalars(params), domain, origins, stream=stream, subbox=subbox)
+
+    def run_views(self, views, scalars: bytes, domain, origins, *, stream=None, subbox=None) -> int:
+        descs = self.make_field_descs(views, origins)
+        return self.run_descs(descs, scalars, domain, stream=stream, subbox=subbox)
+
+    def run_descs(self, descs, scalars: bytes, domain, *, stream=None, subbox=None) -> int:
+        lib = load_library()
+        dom = (ctypes.c_int32 * 3)(*[int(d) for d in domain])
+        sb = (ctypes.c_int32 * 4)(*[int(x) for x in subbox]) if subbox is not None else None
+        if stream is None:
+            stream = current_stream_handle()
+        n = check(lib.b200_stencil_run(self.handle, descs, len(self._api), scalars, len(scalars), dom, sb, ctypes.c_void_p(stream)))
+        self.last_launches = n
+        return n
+
+    def __del__(self):
+        try:
+            if self._handle is not None and _lib is not None:
+                _lib.b200_stencil_unload(self._handle)
+        except Exception:
+            pass

@@ -1,0 +1,367 @@
+"""Stand-alone stencil object of the b200 backend (host-side mirror of gt4py's `StencilObject`).
+
+Where gt4py is installed, `backend="b200"` produces a real `gt4py.cartesian.StencilObject` subclass
+(see `backend.py`).  This module provides the same call surface *without* gt4py, built from a
+serialised stencil IR, so that a machine that only has the lowered IR (tests/golden/ir/*.json), the
+launcher and a GPU can run, test and benchmark the hot path.  It restates the run-path logic of the
+reference:
+
+* `__call__(fields…, params…, domain=None, origin=None, validate_args=True, exec_info=None)`
+                                         (reference: backend/templates/stencil_module.py.in:91-158)
+* `_call_run`: array extraction incl. `__gt_dims__` / `__gt_origin__`, origin normalisation, maximum
+  domain inference, validation with the reference's error types and messages, per-call cache
+                                         (reference: stencil_object.py:69-93, 296-612)
+* `freeze(origin=…, domain=…)` -> `FrozenStencil` skipping all of the above
+                                         (reference: stencil_object.py:96-136, 614-643)
+"""
+
+from __future__ import annotations
+
+import sys
+import time
+import warnings
+from typing import Any, Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import runtime, storage as b2storage
+
+
+class FieldInfo:
+    def __init__(self, d: Dict[str, Any]):
+        self.access = d["access"]
+        self.boundary = tuple((int(lo), int(hi)) for lo, hi in d["boundary"])
+        self.axes = tuple(d["axes"])
+        self.data_dims = tuple(int(x) for x in d["data_dims"])
+        self.dtype = np.dtype(d["dtype"])
+        self.domain_mask = tuple(a in self.axes for a in "IJK")
+        self.domain_ndim = len(self.axes)
+        self.ndim = len(self.axes) + len(self.data_dims)
+
+    def __repr__(self):
+        return f"FieldInfo(access={self.access}, boundary={self.boundary}, axes={self.axes}, data_dims={self.data_dims}, dtype={self.dtype})"
+
+
+class ParameterInfo:
+    def __init__(self, d: Dict[str, Any]):
+        self.access = d["access"]
+        self.dtype = np.dtype(d["dtype"])
+
+
+def _filter_mask(seq, mask):
+    return tuple(s for s, m in zip(seq, mask) if m)
+
+
+class _ArgInfo:
+    __slots__ = ("view", "origin", "dimensions")
+
+    def __init__(self, view, origin, dimensions):
+        self.view, self.origin, self.dimensions = view, origin, dimensions
+
+
+def extract_array_infos(field_args: Dict[str, Any]) -> Dict[str, Optional[_ArgInfo]]:
+    """reference: stencil_object.py:69-93 (without cupy): honour __gt_dims__ / __gt_origin__."""
+    out: Dict[str, Optional[_ArgInfo]] = {}
+    for name, arg in field_args.items():
+        if arg is None:
+            out[name] = None
+            continue
+        view = runtime.as_view(arg)
+        dims = getattr(arg, "__gt_dims__", None)
+        if dims is not None:
+            dims = tuple(str(d) for d in dims)
+            sorted_dims = [d for d in "IJK" if d in dims]
+            sorted_dims += [str(d) for d in sorted(int(d) for d in dims if str(d).isdigit())]
+            view = view.transpose([dims.index(d) for d in sorted_dims])
+            dims = tuple(sorted_dims)
+        origin = getattr(arg, "__gt_origin__", None)
+        out[name] = _ArgInfo(view, tuple(int(o) for o in origin) if origin is not None else None, dims)
+    return out
+
+
+class B200Stencil:
+    """A compiled stencil callable like a gt4py StencilObject."""
+
+    backend = "b200"
+
+    def __init__(self, stencil_ir: Dict[str, Any], options: Optional[Dict[str, Any]] = None, *, name: Optional[str] = None):
+        self.ir = stencil_ir
+        self.name = name or stencil_ir["name"]
+        self.backend_options = dict(options or {})
+        self.compiled = runtime.CompiledStencil(stencil_ir, self.backend_options, name=self.name)
+        self.field_info: Dict[str, Optional[FieldInfo]] = {
+            n: (FieldInfo(fi) if fi is not None else None) for n, fi in stencil_ir["field_info"].items()
+        }
+        self.parameter_info: Dict[str, Optional[ParameterInfo]] = {
+            n: (ParameterInfo(pi) if pi is not None else None) for n, pi in stencil_ir["parameter_info"].items()
+        }
+        self.min_k = int(stencil_ir["domain_info"]["min_k"])
+        self._signature = [p["name"] for p in stencil_ir["params"]]
+        self._field_names = [p["name"] for p in stencil_ir["params"] if p["t"] == "field"]
+        self._param_names = [p["name"] for p in stencil_ir["params"] if p["t"] == "scalar"]
+        # arguments pruned by the frontend still belong to the call signature
+        for n in stencil_ir["field_info"]:
+            if n not in self._signature:
+                self._signature.append(n)
+                self._field_names.append(n)
+        for n in stencil_ir["parameter_info"]:
+            if n not in self._signature:
+                self._signature.append(n)
+                self._param_names.append(n)
+        self._cache: Dict[int, Tuple[tuple, dict]] = {}
+        self.device_sync = bool(self.backend_options.get("device_sync", True))
+
+    # ---- normalisation helpers (reference: stencil_object.py:265-340, 497-529) --------------------
+    @staticmethod
+    def _make_origin_dict(origin) -> Dict[str, Tuple[int, ...]]:
+        try:
+            if isinstance(origin, dict):
+                return dict(origin)
+            if origin is None:
+                return {}
+            if isinstance(origin, (tuple, list)) and all(isinstance(o, (int, np.integer)) for o in origin):
+                return {"_all_": tuple(int(o) for o in origin)}
+        except Exception:
+            pass
+        raise ValueError(f"Invalid 'origin' value ({origin})")
+
+    def _normalize_origins(self, infos, origin) -> Dict[str, Tuple[int, ...]]:
+        origin = self._make_origin_dict(origin)
+        all_origin = origin.get("_all_")
+        for name, fi in self.field_info.items():
+            if fi is None:
+                continue
+            assert name in infos, f"Missing value for '{name}' field."
+            fo = origin.get(name)
+            if fo is not None:
+                if len(fo) != fi.ndim:
+                    assert len(fo) == fi.domain_ndim, f"Invalid origin specification ({fo}) for '{name}' field."
+                    origin[name] = (*fo, *((0,) * len(fi.data_dims)))
+            elif all_origin is not None:
+                origin[name] = (*_filter_mask(all_origin, fi.domain_mask), *((0,) * len(fi.data_dims)))
+            elif infos.get(name) is not None and infos[name].origin is not None:
+                origin[name] = infos[name].origin
+            else:
+                origin[name] = (0,) * fi.ndim
+        return origin
+
+    def _get_max_domain(self, infos, origin, *, only=None, squeeze=True) -> Tuple[int, ...]:
+        big = sys.maxsize
+        max_domain = [big, big, big]
+        for name, fi in self.field_info.items():
+            if fi is None or fi.access == "NONE" or (only is not None and name != only):
+                continue
+            info = infos.get(name)
+            assert info is not None, f"Invalid value for '{name}' field."
+            upper = [b[1] for b, m in zip(fi.boundary, fi.domain_mask) if m]
+            fo = origin[name]
+            ax = 0
+            for a in range(3):
+                if fi.domain_mask[a]:
+                    max_domain[a] = min(max_domain[a], info.view.shape[ax] - (fo[ax] + upper[ax]))
+                    ax += 1
+        if squeeze:
+            return tuple(d if d != big else 1 for d in max_domain)
+        return tuple(max_domain)
+
+    def _validate_args(self, infos, params, domain, origin) -> None:
+        """reference: stencil_object.py:342-494 — same checks, same exception types/messages."""
+        if len(domain) != 3:
+            raise ValueError(f"Invalid 'domain' value '{domain}'")
+        try:
+            domain = tuple(int(d) for d in domain)
+        except Exception as ex:
+            raise ValueError(f"Invalid 'domain' value ({domain})") from ex
+        if not all(d > 0 for d in domain):
+            raise ValueError(f"Compute domain contains zero sizes '{domain}')")
+        max_domain = self._get_max_domain(infos, origin, squeeze=False)
+        if not all(d <= m for d, m in zip(domain, max_domain)):
+            offending = []
+            for name, fi in self.field_info.items():
+                if fi is None or fi.access == "NONE":
+                    continue
+                used = self._get_max_domain(infos, origin, only=name, squeeze=False)
+                if any(u < d for u, d in zip(used, domain)):
+                    offending.append((name, used))
+            raise ValueError(
+                f"Compute domain too large for stencil {self.name}: \n"
+                f"  Stencil domain is {domain} but field indexation leads to read outside of bounds.\n"
+                f"  Check region/horizontal offsets or interval/vertical offsets, or stencil domain.\n"
+                f"  Offending fields (name, size with offset removed): {offending}"
+            )
+        if domain[2] < self.min_k:
+            raise ValueError(
+                f"Compute domain too small. Sequential axis is {domain[2]}, but must be at least {self.min_k}."
+            )
+        for name, fi in self.field_info.items():
+            if fi is None or fi.access == "NONE":
+                continue
+            if name not in infos or infos[name] is None:
+                raise ValueError(f"Missing value for '{name}' field.")
+            info = infos[name]
+            dims = tuple(list(fi.axes) + [str(d) for d in range(len(fi.data_dims))])
+            if not _strides_follow_layout(info.view.strides, dims):
+                warnings.warn(
+                    f"The layout of the field '{name}' is not recommended for this backend."
+                    f"This may lead to performance degradation. Please consider using the"
+                    f"provided allocators in `gt4py.storage`.",
+                    stacklevel=3,
+                )
+            if info.view.dtype != fi.dtype:
+                raise TypeError(f"The dtype of field '{name}' is '{info.view.dtype}' instead of '{fi.dtype}'")
+            if info.view.ndim != fi.domain_ndim + len(fi.data_dims):
+                raise ValueError(
+                    f"Storage for '{name}' has {info.view.ndim} dimensions but the API signature "
+                    f"expects {fi.domain_ndim + len(fi.data_dims)} ('{fi.axes}[{fi.data_dims}]')"
+                )
+            if info.dimensions is not None and dims != info.dimensions:
+                raise ValueError(
+                    f"Storage for '{name}' has dimensions '{info.dimensions}' but the API signature "
+                    f"expects '[{', '.join(fi.axes)}]'"
+                    + (f" and {len(fi.data_dims)}" if fi.data_dims else "")
+                )
+            if tuple(info.view.shape[fi.domain_ndim :]) != fi.data_dims:
+                raise ValueError(
+                    f"Field '{name}' expects data dimensions {fi.data_dims} but got {info.view.shape[fi.domain_ndim:]}"
+                )
+            lower = [b[0] for b, m in zip(fi.boundary, fi.domain_mask) if m]
+            upper = [b[1] for b, m in zip(fi.boundary, fi.domain_mask) if m]
+            fo = origin[name][: fi.domain_ndim]
+            if any(o < lo for o, lo in zip(fo, lower)):
+                full_min = tuple(b[0] if m else 0 for b, m in zip(fi.boundary, fi.domain_mask))
+                raise ValueError(f"Origin for field {name} too small. Must be at least {full_min}, is {tuple(fo)}")
+            spatial = _filter_mask(domain, fi.domain_mask)
+            min_shape = tuple(lb + d + ub for lb, d, ub in zip(lower, spatial, upper))
+            if min_shape > tuple(info.view.shape):
+                raise ValueError(
+                    f"Shape of field {name} is {info.view.shape} but must be at least {min_shape} for given domain and origin."
+                )
+        for name, pi in self.parameter_info.items():
+            if pi is None or pi.access == "NONE":
+                continue
+            if name not in params:
+                raise ValueError(f"Missing value for '{name}' parameter.")
+            if np.dtype(type(params[name])) != pi.dtype:
+                raise TypeError(f"The type of parameter '{name}' is '{type(params[name])}' instead of '{pi.dtype}'")
+
+    # ---- call path -------------------------------------------------------------------------------
+    def __call__(self, *args, domain=None, origin=None, validate_args=True, exec_info=None, **kwargs):
+        if exec_info is not None:
+            exec_info["call_start_time"] = time.perf_counter()
+        if len(args) > len(self._signature):
+            raise TypeError(f"{self.name}() takes {len(self._signature)} positional arguments but {len(args)} were given")
+        bound = dict(zip(self._signature, args))
+        for k, v in kwargs.items():
+            if k in bound:
+                raise TypeError(f"{self.name}() got multiple values for argument '{k}'")
+            if k not in self._signature:
+                raise TypeError(f"{self.name}() got an unexpected keyword argument '{k}'")
+            bound[k] = v
+        field_args = {n: bound.get(n) for n in self._field_names}
+        param_args = {n: bound[n] for n in self._param_names if n in bound}
+        self._call_run(field_args, param_args, domain, origin, validate_args=validate_args, exec_info=exec_info)
+        if exec_info is not None:
+            exec_info["call_end_time"] = time.perf_counter()
+
+    def _call_run(self, field_args, parameter_args, domain, origin, *, validate_args=True, exec_info=None):
+        if exec_info is not None:
+            exec_info["call_run_start_time"] = time.perf_counter()
+        infos = extract_array_infos(field_args)
+        key = hash(
+            (
+                tuple((n, i.view.shape, i.origin or (0, 0, 0)) for n, i in infos.items() if i is not None),
+                *parameter_args.keys(),
+                repr(domain),
+                repr(origin),
+            )
+        )
+        cached = self._cache.get(key)
+        if cached is None:
+            origin = self._normalize_origins(infos, origin)
+            if domain is None:
+                domain = self._get_max_domain(infos, origin)
+            if validate_args:
+                self._validate_args(infos, parameter_args, domain, origin)
+            self._cache[key] = (tuple(domain), origin)
+        else:
+            domain, origin = cached
+        views = {n: (i.view if i is not None else None) for n, i in infos.items()}
+        self.run(_domain_=tuple(domain), _origin_=origin, exec_info=exec_info, **views, **parameter_args)
+        if exec_info is not None:
+            exec_info["call_run_end_time"] = time.perf_counter()
+
+    def run(self, _domain_, _origin_, exec_info=None, *, stream=None, subbox=None, **args):
+        """reference: stencil_module.py.in:160-169 (native call + optional device sync)."""
+        if exec_info is not None:
+            exec_info["domain"] = _domain_
+            exec_info["origin"] = _origin_
+            exec_info["run_start_time"] = time.perf_counter()
+        fields = {n: args.get(n) for n in self._field_names}
+        params = {n: args[n] for n in self._param_names if n in args}
+        n = self.compiled.run(fields, params, _domain_, _origin_, stream=stream, subbox=subbox)
+        if self.device_sync:
+            runtime.check(runtime.load_library().b200_stream_synchronize(stream if stream is not None else runtime.current_stream_handle()))
+        if exec_info is not None:
+            exec_info["run_end_time"] = time.perf_counter()
+            exec_info["b200_kernel_launches"] = n
+        return n
+
+    def freeze(self, *, origin: Dict[str, Tuple[int, ...]], domain: Tuple[int, ...]) -> "FrozenStencil":
+        return FrozenStencil(self, origin, tuple(domain))
+
+    def clean_call_args_cache(self) -> None:
+        self._cache.clear()
+
+
+class FrozenStencil:
+    """Pre-resolved origin/domain and pre-built field descriptors: the low-overhead launch path
+    (reference: stencil_object.py:96-136).  Descriptors are rebuilt only when an argument's
+    (pointer, shape, strides) changes."""
+
+    def __init__(self, stencil: B200Stencil, origin, domain):
+        for name, fi in stencil.field_info.items():
+            if fi is None:
+                continue
+            if name not in origin or len(origin[name]) != fi.ndim:
+                raise ValueError(f"'{name}' origin {origin.get(name)} is not a {fi.ndim}-dimensional integer tuple")
+        self.stencil_object = stencil
+        self.origin = origin
+        self.domain = domain
+        self._key = None
+        self._descs = None
+        self._scal_key = None
+        self._scal = None
+
+    def __call__(self, *, exec_info=None, stream=None, subbox=None, **kwargs) -> int:
+        st = self.stencil_object
+        views = {n: (runtime.as_view(kwargs[n]) if kwargs.get(n) is not None else None) for n in st._field_names}
+        key = tuple((v.ptr, v.shape, v.strides) if v is not None else None for v in views.values())
+        if key != self._key:
+            self._descs = st.compiled.make_field_descs(views, self.origin)
+            self._key = key
+        skey = tuple(kwargs.get(n) for n in st._param_names)
+        if skey != self._scal_key:
+            self._scal = st.compiled.pack_scalars({n: kwargs.get(n) for n in st._param_names})
+            self._scal_key = skey
+        n = st.compiled.run_descs(self._descs, self._scal, self.domain, stream=stream, subbox=subbox)
+        if st.device_sync:
+            runtime.check(runtime.load_library().b200_stream_synchronize(stream if stream is not None else runtime.current_stream_handle()))
+        return n
+
+
+def _strides_follow_layout(strides, dims) -> bool:
+    lm = b2storage.layout_map(dims)
+    if len(strides) != len(lm):
+        return False
+    stride = 0
+    for dim in reversed(np.argsort(lm)):
+        if strides[dim] < stride:
+            return False
+        stride = strides[dim]
+    return True
+
+
+def from_ir_file(path, options=None) -> B200Stencil:
+    from . import ir as b2ir
+
+    return B200Stencil(b2ir.load_file(path), options)

@@ -1,0 +1,323 @@
+"""Device storage of the b200 backend: `gt4py.storage`'s allocator contract without cupy.
+
+Mirrors the reference's layout-aware allocation
+(reference: src/gt4py/storage/cartesian/interface.py:40-327 `empty/zeros/ones/full/from_array`,
+storage/allocators.py:187-273 `NDArrayBufferAllocator.allocate`, storage/cartesian/layout.py:21-76,
+storage/cartesian/utils.py:84-165 `normalize_storage_spec`) for the `b200` preset:
+
+* layout base (2, 1, 0): I is the unit-stride axis, then J, K outermost; data dimensions outermost
+  of all (same preset as `gt:gpu`, layout_registry.py:105-113) — every warp reads 128-byte lines
+  along I and the K-march of a column kernel is a constant stride
+* alignment 32 *elements*: the contiguous axis is padded to a multiple of 32 elements and the
+  element at `aligned_index` (normally the compute-domain origin) sits on a 32-element boundary,
+  so interior rows start 128-B (fp32) / 256-B (fp64) aligned -> `float4` / TMA friendly.
+
+Memory comes from torch's CUDA caching allocator (plumbing); the returned `DeviceArray` is a small
+ndarray-like (shape / byte strides / numpy dtype / `__cuda_array_interface__` / slicing /
+assignment) so that it satisfies what `StencilObject` and user code expect from a gt4py storage.
+"""
+
+from __future__ import annotations
+
+import math
+import numbers
+from typing import Any, Optional, Sequence, Tuple
+
+import numpy as np
+
+ALIGNMENT_ELEMENTS = 32
+BASE_LAYOUT = (2, 1, 0)
+
+_TORCH_DTYPES = None
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _torch_dtype(dtype: np.dtype):
+    global _TORCH_DTYPES
+    torch = _torch()
+    if _TORCH_DTYPES is None:
+        _TORCH_DTYPES = {
+            np.dtype("bool"): torch.bool,
+            np.dtype("int8"): torch.int8,
+            np.dtype("int16"): torch.int16,
+            np.dtype("int32"): torch.int32,
+            np.dtype("int64"): torch.int64,
+            np.dtype("uint8"): torch.uint8,
+            np.dtype("float32"): torch.float32,
+            np.dtype("float64"): torch.float64,
+        }
+    try:
+        return _TORCH_DTYPES[np.dtype(dtype)]
+    except KeyError:
+        raise TypeError(f"b200 storage: unsupported dtype {dtype}") from None
+
+
+# ---- layout (reference: storage/cartesian/layout.py:28-57, 60-76) -------------------------------
+def layout_map(dimensions: Sequence[str], base_layout: Tuple[int, ...] = BASE_LAYOUT) -> Tuple[int, ...]:
+    """Layout map for `dimensions` (subset of I, J, K followed by data dims '0', '1', …).
+
+    Larger value = smaller stride. Cartesian axes follow `base_layout`, data dims are outermost.
+    """
+    mask = [d in dimensions for d in "IJK"]
+    ranks = [bl for m, bl in zip(mask, base_layout) if m]
+    n_data = len(dimensions) - sum(mask)
+    ranks = [n_data + r for r in ranks] + list(range(n_data))
+    res = [0] * len(ranks)
+    for i, idx in enumerate(np.argsort(ranks)):
+        res[idx] = i
+    return tuple(res)
+
+
+def is_optimal_layout(field: Any, dimensions: Sequence[str]) -> bool:
+    strides = getattr(field, "strides", None)
+    if callable(strides):  # torch.Tensor.stride()
+        strides = field.stride()
+    lm = layout_map(tuple(dimensions))
+    if strides is None or len(strides) != len(lm):
+        return False
+    stride = 0
+    for dim in reversed(np.argsort(lm)):
+        if strides[dim] < stride:
+            return False
+        stride = strides[dim]
+    return True
+
+
+def default_dimensions(ndim: int) -> Tuple[str, ...]:
+    return tuple("IJK"[:ndim]) if ndim <= 3 else tuple("IJK") + tuple(str(d) for d in range(ndim - 3))
+
+
+def normalize_storage_spec(aligned_index, shape, dtype, dimensions):
+    """Same contract (and error types) as reference storage/cartesian/utils.py:84-165."""
+    if shape is None or isinstance(shape, (str, bytes)) or not hasattr(shape, "__iter__"):
+        raise TypeError("shape must be an iterable of ints.")
+    shape = tuple(shape)
+    if not all(isinstance(s, numbers.Integral) for s in shape):
+        raise TypeError("shape must be an iterable of ints.")
+    if dimensions is None:
+        dimensions = default_dimensions(len(shape))
+    dimensions = tuple(str(getattr(d, "__gt_axis_name__", d)) for d in dimensions)
+    if not all(d.isdigit() or d in "IJK" for d in dimensions):
+        raise ValueError(f"Invalid dimensions definition: '{dimensions}'")
+    if len(shape) != len(dimensions):
+        raise ValueError(f"Dimensions ({dimensions}) and shape ({shape}) have non-matching sizes.")
+    if any(s <= 0 for s in shape):
+        raise ValueError(f"shape ({shape}) contains non-positive value.")
+    if aligned_index is None:
+        aligned_index = (0,) * len(shape)
+    if isinstance(aligned_index, (str, bytes)) or not hasattr(aligned_index, "__iter__"):
+        raise TypeError("aligned_index must be an iterable of ints.")
+    aligned_index = tuple(aligned_index)
+    if not all(isinstance(i, numbers.Integral) for i in aligned_index):
+        raise TypeError("aligned_index must be an iterable of ints.")
+    if len(aligned_index) != len(shape):
+        raise ValueError(f"Shape ({shape}) and aligned_index ({aligned_index}) have non-matching sizes.")
+    if any(i < 0 for i in aligned_index):
+        raise ValueError(f"aligned_index ({aligned_index}) contains negative value.")
+    dtype = np.dtype(dtype)
+    if dtype.shape:
+        sub_dtype, sub_shape = dtype.subdtype
+        aligned_index = (*aligned_index, *((0,) * dtype.ndim))
+        shape = (*shape, *sub_shape)
+        dimensions = (*dimensions, *(str(d) for d in range(dtype.ndim)))
+        dtype = sub_dtype
+    return aligned_index, shape, dtype, dimensions
+
+
+def compute_layout(shape, lmap, itemsize: int, alignment_elems: int, aligned_index):
+    """-> (element strides, padded element count, lead offset in elements).
+
+    Follows reference allocators.py:205-254: pad the unit-stride axis to a multiple of the
+    alignment, strides from the layout map, shift so that `aligned_index` is aligned.
+    """
+    ndim = len(shape)
+    if ndim == 0:
+        return (), 1, 0
+    order = [lmap.index(i) for i in range(ndim)]  # slowest ... fastest
+    padded = list(int(s) for s in shape)
+    fast = order[-1]
+    padded[fast] = math.ceil(shape[fast] / alignment_elems) * alignment_elems
+    strides = [1] * ndim
+    acc = 1
+    for n in range(ndim - 2, -1, -1):
+        acc = strides[order[n]] = acc * padded[order[n + 1]]
+    total = int(np.prod(padded))
+    lead = (math.ceil(aligned_index[fast] / alignment_elems) * alignment_elems - aligned_index[fast]) % alignment_elems
+    return tuple(strides), total, lead
+
+
+class DeviceArray:
+    """ndarray-like view of device memory (I-contiguous pitched buffer owned by a torch tensor)."""
+
+
+    def __init__(self, base, offset: int, shape, estrides, dtype):
+        self._base = base  # 1-D torch tensor of `dtype` on the device
+        self._offset = int(offset)  # element offset of [0, 0, …]
+        self.shape = tuple(int(s) for s in shape)
+        self._estrides = tuple(int(s) for s in estrides)
+        self.dtype = np.dtype(dtype)
+
+    # -- ndarray-like surface ------------------------------------------------------------------
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    @property
+    def itemsize(self) -> int:
+        return self.dtype.itemsize
+
+    @property
+    def strides(self) -> Tuple[int, ...]:
+        return tuple(s * self.dtype.itemsize for s in self._estrides)
+
+    @property
+    def element_strides(self) -> Tuple[int, ...]:
+        return self._estrides
+
+    @property
+    def data_ptr(self) -> int:
+        return self._base.data_ptr() + self._offset * self.dtype.itemsize
+
+    @property
+    def device(self):
+        return self._base.device
+
+    @property
+    def __cuda_array_interface__(self):
+        return {
+            "shape": self.shape,
+            "typestr": self.dtype.str,
+            "data": (self.data_ptr, False),
+            "strides": self.strides,
+            "version": 3,
+        }
+
+    def torch(self):
+        """Zero-copy strided torch view."""
+        return _torch().as_strided(self._base, self.shape, self._estrides, self._offset)
+
+    def get(self) -> np.ndarray:
+        """Copy to host (like cupy.ndarray.get)."""
+        return self.torch().cpu().numpy()
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.get()
+        return out.astype(dtype) if dtype is not None else out
+
+    def _view(self, t) -> "DeviceArray":
+        return DeviceArray(self._base, t.storage_offset(), tuple(t.shape), tuple(t.stride()), self.dtype)
+
+    def __getitem__(self, key):
+        return self._view(self.torch()[key])
+
+    def __setitem__(self, key, value):
+        torch = _torch()
+        if isinstance(value, DeviceArray):
+            value = value.torch()
+        elif isinstance(value, np.ndarray):
+            value = torch.from_numpy(np.ascontiguousarray(value)).to(self._base.device, non_blocking=False)
+        elif hasattr(value, "__cuda_array_interface__") and not isinstance(value, torch.Tensor):
+            value = torch.as_tensor(value, device=self._base.device)
+        elif isinstance(value, (list, tuple)):
+            value = torch.as_tensor(np.asarray(value)).to(self._base.device)
+        if isinstance(value, torch.Tensor):
+            value = value.to(dtype=_torch_dtype(self.dtype))
+        self.torch()[key] = value
+
+    def transpose(self, *axes):
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        if not axes:
+            axes = tuple(reversed(range(self.ndim)))
+        return DeviceArray(
+            self._base, self._offset, tuple(self.shape[a] for a in axes), tuple(self._estrides[a] for a in axes), self.dtype
+        )
+
+    def fill(self, value) -> None:
+        self.torch().fill_(value)
+
+    def copy(self) -> "DeviceArray":
+        out = empty(self.shape, self.dtype)
+        out[...] = self
+        return out
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __repr__(self):
+        return f"DeviceArray(shape={self.shape}, dtype={self.dtype}, strides={self.strides}, device={self.device})"
+
+
+def _device(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200 storage: no CUDA device available (the b200 backend has no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+
+def allocate(shape, lmap, dtype, alignment_elems: int, aligned_index, *, device=None, fill=None) -> DeviceArray:
+    torch = _torch()
+    dtype = np.dtype(dtype)
+    estrides, total, lead = compute_layout(shape, lmap, dtype.itemsize, alignment_elems, aligned_index)
+    align_bytes = max(alignment_elems * dtype.itemsize, 256)
+    nbytes = (total + lead) * dtype.itemsize + align_bytes
+    raw = torch.empty(nbytes, dtype=torch.uint8, device=_device(device))
+    mis = (-raw.data_ptr()) % align_bytes
+    end = mis + (total + lead) * dtype.itemsize
+    base = raw[mis:end].view(_torch_dtype(dtype))
+    arr = DeviceArray(base, lead, shape, estrides, dtype)
+    if fill is not None:
+        base.fill_(fill)
+    return arr
+
+
+# ---- public constructors (reference: storage/cartesian/interface.py:40-327) --------------------
+def empty(shape, dtype=np.float64, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None, _fill=None):
+    if backend != "b200":
+        raise RuntimeError(f"Storage preset '{backend}' is not handled by gt4py_b200.storage.")
+    aligned_index, shape, dtype, dimensions = normalize_storage_spec(aligned_index, shape, dtype, dimensions)
+    return allocate(shape, layout_map(dimensions), dtype, ALIGNMENT_ELEMENTS, aligned_index, device=device, fill=_fill)
+
+
+def zeros(shape, dtype=np.float64, **kwargs):
+    return empty(shape, dtype, _fill=0, **kwargs)
+
+
+def ones(shape, dtype=np.float64, **kwargs):
+    return empty(shape, dtype, _fill=1, **kwargs)
+
+
+def full(shape, fill_value, dtype=np.float64, **kwargs):
+    return empty(shape, dtype, _fill=fill_value, **kwargs)
+
+
+def from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None):
+    src = data.get() if isinstance(data, DeviceArray) else np.asarray(data)
+    shape = src.shape
+    if dtype is None:
+        dtype = src.dtype
+    dtype = np.dtype(dtype)
+    if dtype.shape:
+        if shape[-dtype.ndim :] != dtype.shape:
+            raise ValueError(f"Incompatible data shape {shape} with dtype of shape {dtype.shape}.")
+        shape = shape[: -dtype.ndim]
+    out = empty(shape, dtype, backend=backend, aligned_index=aligned_index, dimensions=dimensions, device=device)
+    out[...] = src.astype(out.dtype, copy=False)
+    return out
+
+
+def cpu_copy(array) -> np.ndarray:
+    if isinstance(array, DeviceArray):
+        return array.get()
+    if hasattr(array, "cpu"):
+        return array.cpu().numpy()
+    return np.array(array)

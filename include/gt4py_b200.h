@@ -1,0 +1,113 @@
+/* gt4py_b200.h — C ABI of the b200 stencil-execution backend (libgt4py_b200.so).
+ *
+ * This is the drop-in boundary of the hot path: the native entry the reference reaches from the
+ * generated module's `run()` (reference: src/gt4py/cartesian/backend/templates/stencil_module.py.in:160-169).
+ * For `gt:gpu` that entry is a per-stencil pybind11 function
+ *     run_computation(std::array<uint,3> domain, {py::object field, std::array<int,ndim> origin}…,
+ *                     scalars…, py::object exec_info)
+ * (reference: backend/gtc_common.py:65-103, 144-168; backend/gtcpp_backend.py:77-99) which reads the
+ * device buffers through __cuda_array_interface__ (gt::as_cuda_sid, gtc_common.py:42-50), shifts
+ * them to the origin and calls gridtools::stencil::run(spec, gpu<>{}, grid, fields…)
+ * (gtc/gtcpp/gtcpp_codegen.py:267-285).  Here the same information crosses a plain C boundary:
+ * pointers, strides, origins, a domain and a blob of scalar parameters.  No Python, torch or CUDA
+ * types appear in the signatures; `stream` is a cudaStream_t passed as void*.
+ *
+ * All functions return 0 on success or a negative b200_status; the message of the last failure on
+ * the calling thread is available from b200_last_error().  Nothing here falls back to the CPU.
+ */
+#ifndef GT4PY_B200_H
+#define GT4PY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+#define B200_MAX_DIMS 5 /* I, J, K + up to two data dimensions */
+
+typedef enum b200_status {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,  /* bad argument / malformed plan                                  */
+  B200_ERR_CUDA = -2,     /* a CUDA runtime call failed (message has the CUDA error string)  */
+  B200_ERR_NO_DEVICE = -3,/* no usable sm_100 device / driver                               */
+  B200_ERR_NCCL = -4,     /* NCCL missing or an NCCL call failed                            */
+  B200_ERR_NOMEM = -5
+} b200_status;
+
+/* One API field of a stencil call — the C form of the (buffer, origin) pairs of the reference's
+ * run_computation (backend/gtc_common.py:144-168).  The launcher borrows `data` for the call. */
+typedef struct b200_field {
+  void* data;                      /* device address of array element [0, 0, 0, …]; NULL = unused argument */
+  int64_t strides[B200_MAX_DIMS];  /* ELEMENT strides of I, J, K, d0, d1 (0 for an axis the field lacks)  */
+  int32_t origin[3];               /* array index of domain point (0,0,0) along I, J, K (0 if axis lacks) */
+  int32_t shape[3];                /* array extents along I, J, K (1 if the field lacks the axis)          */
+} b200_field_t;
+
+typedef struct b200_stencil b200_stencil_t; /* a loaded stencil: device code + launch plan + scratch */
+typedef struct b200_comm b200_comm_t;       /* an NCCL communicator for halo exchanges               */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int b200_abi_version(void);
+const char* b200_last_error(void);
+/* Number of CUDA devices; sets *sm_major/*sm_minor of `device` when non-NULL. */
+int b200_device_info(int device, int* n_devices, int* sm_major, int* sm_minor, int* n_sms);
+
+/* ---- stencil lifecycle (replaces: importing the per-stencil pybind11 extension,
+ *      reference backend/gtc_common.py:215-261 + backend/pyext_builder.py) ---------------------- */
+/* `image` is an sm_100a cubin produced by the b200 code generator; `plan_text` its launch plan
+ * (gt4py_b200.codegen.plan_to_text).  Both are copied. */
+int b200_stencil_load(const void* image, size_t image_size, const char* plan_text, b200_stencil_t** out);
+int b200_stencil_unload(b200_stencil_t* st);
+int b200_stencil_num_fields(const b200_stencil_t* st);   /* API fields expected by run()            */
+size_t b200_stencil_scalars_size(const b200_stencil_t* st);
+int b200_stencil_num_kernels(const b200_stencil_t* st);
+/* name of kernel `index` (for profiling tools); NULL when out of range */
+const char* b200_stencil_kernel_name(const b200_stencil_t* st, int index);
+
+/* ---- the hot path: one stencil application (replaces run_computation → gridtools run) -------- */
+/* fields    : `nfields` API fields in stencil-signature order
+ * scalars   : scalar parameters packed by the layout in the plan (`scalars_size` bytes)
+ * domain    : compute domain (nI, nJ, nK)
+ * subbox    : NULL for the whole domain, else {i_lo, i_hi, j_lo, j_hi} in domain coordinates — the
+ *             horizontal part of the domain this call computes (used to split interior / boundary
+ *             when overlapping a halo exchange)
+ * stream    : cudaStream_t; kernels are enqueued, the call does not synchronise
+ * returns the number of kernel launches enqueued (>= 0) or a negative status */
+int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
+                     size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], void* stream);
+
+/* ---- streams / events (device-side timing for exec_info and bench) --------------------------- */
+int b200_stream_create(void** stream);
+int b200_stream_destroy(void* stream);
+int b200_stream_synchronize(void* stream);
+int b200_event_create(void** event);
+int b200_event_destroy(void* event);
+int b200_event_record(void* event, void* stream);
+int b200_stream_wait_event(void* stream, void* event);
+int b200_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
+
+/* ---- multi-GPU halo exchange over NCCL (an addition: the reference has no distributed path) --- */
+#define B200_NCCL_UNIQUE_ID_BYTES 128
+int b200_comm_unique_id(void* id_out /* B200_NCCL_UNIQUE_ID_BYTES */);
+int b200_comm_init(b200_comm_t** out, const void* unique_id, int n_ranks, int rank);
+int b200_comm_destroy(b200_comm_t* comm);
+/* One J-slab halo exchange for one field, enqueued on `stream` inside a single NCCL group:
+ * send `count` bytes at send_lo to rank-1 / send_hi to rank+1, receive into recv_lo / recv_hi.
+ * A negative peer (domain edge) skips that side. */
+typedef struct b200_halo {
+  const void* send_lo; void* recv_lo;   /* exchanged with `peer_lo` */
+  const void* send_hi; void* recv_hi;   /* exchanged with `peer_hi` */
+  size_t bytes;
+} b200_halo_t;
+int b200_halo_exchange(b200_comm_t* comm, const b200_halo_t* halos, int n_halos, int peer_lo, int peer_hi, void* stream);
+/* Strided slab <-> contiguous staging buffer copy kernels (J-halo slabs of a (2,1,0)-layout field
+ * are nK separate chunks): rows × row_bytes, source/destination pitch in bytes. */
+int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GT4PY_B200_H */

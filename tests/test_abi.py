@@ -1,0 +1,52 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/gt4py_b200.h declares; entry points fail loudly (never fall back) without a device."""
+
+import ctypes
+import pathlib
+import re
+
+import pytest
+
+from gt4py_b200 import jit, runtime
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "gt4py_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    jit.build_launcher()
+    lib = ctypes.CDLL(str(runtime.LIB_PATH))
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in gt4py_b200.h but not exported"
+    assert set(syms) == set(runtime.EXPORTED_SYMBOLS)
+    assert runtime.load_library().b200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    from gt4py_b200 import storage, testing
+    from gt4py_b200.stencil import B200Stencil
+
+    with pytest.raises(RuntimeError):
+        storage.zeros((4, 4, 4))
+    st = B200Stencil(testing.load_ir("copy_f64"))  # code generation + nvcc work without a GPU
+    view = runtime.ArrayView(0x1000, (4, 4, 4), (1, 4, 16), "float64")
+    with pytest.raises(runtime.B200Error):
+        st.compiled.run_views({"a": view, "b": view}, b"", (2, 2, 2), {"a": (0, 0, 0), "b": (0, 0, 0)}, stream=0)
+
+
+def test_bad_plan_is_rejected():
+    lib = runtime.load_library()
+    h = ctypes.c_void_p()
+    rc = lib.b200_stencil_load(b"xx", 2, b"not a plan", ctypes.byref(h))
+    assert rc < 0 and b"plan" in lib.b200_last_error()

@@ -1,0 +1,108 @@
+"""-m gpu: the CUDA path (through the C-ABI launcher) against the oracle and the reference goldens."""
+
+import numpy as np
+import pytest
+
+from gt4py_b200 import storage, testing
+
+from parity_util import run_case
+
+pytestmark = pytest.mark.gpu
+CASES = testing.list_cases()
+
+
+@pytest.mark.parametrize("variant", ["default", "staged"])
+@pytest.mark.parametrize("name", CASES)
+def test_fixture_parity_point_generator(name, variant):
+    """Every fixture, baseline generator, vs oracle AND vs the stored outputs of the reference."""
+    run_case(name, variant, {"strategy": "point"}, check_golden=True)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fixture_parity_auto_strategy(name):
+    """What `backend="b200"` picks by default (streaming kernels where applicable)."""
+    run_case(name, "staged", {"strategy": "auto"}, check_golden=True)
+    run_case(name, "default", {"strategy": "auto"}, seed=1, check_golden=True)
+
+
+@pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32"])
+@pytest.mark.parametrize("domain", [(1, 1, 1), (3, 2, 1), (127, 5, 2), (129, 33, 3), (260, 70, 4)])
+def test_ragged_domains(name, domain):
+    for variant in ("default", "staged"):
+        run_case(name, variant, None, domain=domain, seed=2)
+
+
+@pytest.mark.parametrize("name", ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64"])
+@pytest.mark.parametrize("domain", [(1, 1, 4), (70, 3, 9), (130, 37, 33)])
+def test_column_solvers_domains(name, domain):
+    run_case(name, "default", None, domain=domain, seed=4)
+
+
+def test_c_order_torch_tensors_any_stride():
+    """Plain C-ordered (K-contiguous) torch tensors must be accepted (reference:
+    tests/cartesian_tests/integration_tests/feature_tests/test_field_layouts.py:31-47); layout only warns."""
+    import torch
+
+    with pytest.warns(UserWarning, match="layout"):
+        run_case("hdiff_f32", "staged", None, to_device=lambda n, a: torch.from_numpy(a).cuda())
+    with pytest.warns(UserWarning, match="layout"):
+        run_case("tridiagonal_f64", "default", None, to_device=lambda n, a: torch.from_numpy(a).cuda())
+
+
+def test_gt_dims_permutation():
+    """__gt_dims__ = ('K','J','I') arrays are transposed to IJK before the call
+    (reference: stencil_object.py:78-92, test_call_interface.py)."""
+    import torch
+
+    class Permuted:
+        def __init__(self, arr):
+            self.t = torch.from_numpy(np.ascontiguousarray(arr.transpose(2, 1, 0))).cuda()
+            self.__gt_dims__ = ("K", "J", "I")
+            self.__cuda_array_interface__ = self.t.__cuda_array_interface__
+
+        def cpu(self):
+            return self.t.permute(2, 1, 0).cpu()
+
+    run_case("laplacian_f64", "default", None, domain=(20, 13, 5), to_device=lambda n, a: Permuted(a))
+
+
+def test_hdiff_full_size_properties():
+    """BASELINE.json configs[1] at full size (1024x1024x80 fp32): size-independent properties.
+    * a constant field is a fixed point of horizontal diffusion (lap == 0 -> out == in), exactly
+    * default and staged lowerings and both generators agree bit for bit on random data
+    * a sub-box of the full run equals the oracle run on that sub-box alone (translation invariance)."""
+    from gt4py_b200.stencil import B200Stencil
+
+    st_s = testing.load_ir("hdiff_f32", "staged")
+    st_d = testing.load_ir("hdiff_f32", "default")
+    n, nk, h = 1024, 80, 2
+    rng = np.random.default_rng(5)
+    shape = (n + 2 * h, n + 2 * h, nk)
+    origin = {k: (h, h, 0) for k in ("in_field", "out_field", "coeff")}
+    inp = storage.from_array(rng.random(shape, dtype=np.float32), aligned_index=(h, h, 0))
+    coeff = storage.from_array(rng.random(shape, dtype=np.float32) * np.float32(0.1), aligned_index=(h, h, 0))
+    outs = []
+    for st, opts in ((st_s, {"strategy": "auto"}), (st_d, {"strategy": "point"}), (st_s, {"strategy": "point"})):
+        out = storage.zeros(shape, np.float32, aligned_index=(h, h, 0))
+        B200Stencil(st, opts)(inp, out, coeff, origin=origin, domain=(n, n, nk))
+        outs.append(out.torch().clone())
+    import torch
+
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    # oracle on a corner sub-box that includes the halo
+    from oracle import numpy_oracle
+
+    sub = 48
+    f = {
+        "in_field": inp.get()[: sub + 2 * h, : sub + 2 * h, :4].copy(),
+        "coeff": coeff.get()[: sub + 2 * h, : sub + 2 * h, :4].copy(),
+        "out_field": np.zeros((sub + 2 * h, sub + 2 * h, 4), np.float32),
+    }
+    numpy_oracle.run(st_d, f, {}, (sub, sub, 4), origin)
+    got = outs[0][h : h + sub, h : h + sub, :4].cpu().numpy()
+    np.testing.assert_array_equal(got, f["out_field"][h : h + sub, h : h + sub, :])
+    # fixed point
+    const = storage.full(shape, 3.25, np.float32, aligned_index=(h, h, 0))
+    out = storage.zeros(shape, np.float32, aligned_index=(h, h, 0))
+    B200Stencil(st_s, None)(const, out, coeff, origin=origin, domain=(n, n, nk))
+    assert torch.equal(out.torch()[h:-h, h:-h, :], const.torch()[h:-h, h:-h, :])

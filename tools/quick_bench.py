@@ -1,0 +1,42 @@
+"""Ad-hoc device timing of fixture stencils (dev tool; bench.py is the contract)."""
+import argparse, json, sys, pathlib
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+from gt4py_b200 import storage, testing
+from gt4py_b200.stencil import B200Stencil
+
+def bench(name, variant, strategy, domain, iters=20, warm=5, extra=None):
+    st = testing.load_ir(name, variant)
+    fields, params, origins, domain = testing.make_case_data(st, name, domain=domain, seed=0)
+    dev = {k: (storage.from_array(v, aligned_index=origins[k]) if v is not None else None) for k, v in fields.items()}
+    opts = {"strategy": strategy, "device_sync": False}; opts.update(extra or {})
+    s = B200Stencil(st, opts)
+    fr = s.freeze(origin=origins, domain=domain)
+    kw = {**dev, **params}
+    for _ in range(warm): fr(**kw)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fr(**kw); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts)); cells = domain[0]*domain[1]*domain[2]
+    bpc = testing.algorithmic_bytes_per_cell(st)
+    return {"name": name, "variant": variant, "strategy": strategy, "domain": domain, "ms": round(ms,4), "min_ms": round(min(ts),4),
+            "mcells_s": round(cells/ms/1e3,1), "gbs": round(cells*bpc/ms/1e6,1), "launches": s.compiled.last_launches, **(extra or {})}
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); a = ap.parse_args()
+    runs = [
+        ("hdiff_f32","default","point",(1024,1024,80)),
+        ("hdiff_f32","staged","point",(1024,1024,80)),
+        ("hdiff_f32","staged","auto",(1024,1024,80)),
+        ("copy_f64","default","point",(1024,1024,40)),
+        ("laplacian_f64","default","point",(1024,1024,40)),
+        ("tridiagonal_f64","default","point",(512,512,160)),
+        ("vadv_f64","default","point",(512,512,80)),
+        ("upwind5_f32","default","point",(2048,2048,20)),
+        ("upwind5_f32","staged","auto",(2048,2048,20)),
+    ]
+    for r in runs:
+        try: print(json.dumps(bench(*r)), flush=True)
+        except Exception as e: print("FAIL", r, repr(e)[:500], flush=True)
