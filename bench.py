@@ -1,0 +1,428 @@
+"""bench.py — headline benchmark of the b200 stencil backend (contract: see the task statement).
+
+Workload (BASELINE.json configs[1]): horizontal diffusion (lap-of-lap + flux limiter,
+reference stencil tests/cartesian_tests/integration_tests/multi_feature_tests/stencil_definitions.py:316-328)
+on a 1024 x 1024 x 80 fp32 domain (fields 1028 x 1028 x 80, origin (2,2,0)), compiled with
+literal_float_precision=32.  One "step" = one application of the stencil over the whole domain.
+
+  value  : Mcell-updates/s with all fields resident in HBM, timed with CUDA events on the
+           launching stream over exactly K steps (max over ranks for N > 1)
+  e2e    : same metric through the public call (`stencil(in, out, coeff, origin=…, domain=…)`)
+           with HOST (pinned) buffers: H2D copy of in_field+coeff and D2H copy of out_field
+           inside the timed region every step
+  roofline: algorithmic bytes (12 B/cell: read in_field, coeff; write out_field) over
+           the kernel's average launch duration, against the measured HBM copy bandwidth of
+           MEASURED_PEAKS.json
+  N > 1  : weak scaling — the global domain is 1024 x (1024*N) x 80, cut into N J-slabs; every step
+           exchanges the two 2-row J-halos of in_field with the neighbour ranks over NCCL (C-ABI
+           b200_halo_exchange) overlapped with the interior of the stencil, then computes the
+           boundary rows.
+
+`--impl reference` times the CPU restatement of the reference numpy backend (oracle/) on a bounded
+sample of the same workload on the host cores (the reference's GridTools CPU backends cannot be
+built offline: gridtools-cpp headers are not vendored).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+NI, NJ, NK, HALO = 1024, 1024, 80, 2
+STENCIL, VARIANT = "hdiff_f32", "staged"
+BYTES_PER_CELL = 12
+METRIC = "Mcell-updates/s + achieved HBM GB/s, horiz-diffusion 1024x1024x80 fp32"
+CPU_SAMPLE = (256, 256, 16)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU baseline: the oracle (numpy restatement of the reference numpy backend) ---------------------
+def cpu_baseline(max_seconds: float = 12.0, min_calls: int = 2):
+    from gt4py_b200 import testing
+    from oracle import numpy_oracle
+
+    st = testing.load_ir(STENCIL, "default")
+    fields, params, origins, domain = testing.make_case_data(st, STENCIL, domain=CPU_SAMPLE, seed=0)
+    numpy_oracle.run(st, fields, params, domain, origins)  # warm-up
+    times = []
+    t_end = time.perf_counter() + max_seconds
+    while len(times) < min_calls or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        numpy_oracle.run(st, fields, params, domain, origins)
+        times.append(time.perf_counter() - t0)
+    cells = domain[0] * domain[1] * domain[2]
+    best = float(np.median(times))
+    return {
+        "value": round(cells / best / 1e6, 3),
+        "unit": "Mcell-updates/s",
+        "cores": 1,
+        "kind": "port",
+        "sample": f"{STENCIL} {domain[0]}x{domain[1]}x{domain[2]} fp32 sub-domain, {len(times)} calls, median; "
+        f"NumPy whole-array ops are single-threaded ({os.cpu_count()} host cores available)",
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # steps/warmup scale the sample: each "step" is one oracle call on the bounded sub-domain
+    from gt4py_b200 import testing
+    from oracle import numpy_oracle
+
+    st = testing.load_ir(STENCIL, "default")
+    fields, params, origins, domain = testing.make_case_data(st, STENCIL, domain=CPU_SAMPLE, seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        numpy_oracle.run(st, fields, params, domain, origins)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        numpy_oracle.run(st, fields, params, domain, origins)
+    dt = time.perf_counter() - t0
+    cells = domain[0] * domain[1] * domain[2]
+    value = round(cells * steps / dt / 1e6, 3)
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "Mcell-updates/s",
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": args.warmup,
+        "ms_per_step": round(dt / steps * 1e3, 3),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"horizontal diffusion {NI}x{NJ}x{NK} fp32 (configs[1]); CPU arm runs a "
+                   f"{domain[0]}x{domain[1]}x{domain[2]} sub-domain per step"},
+        "cpu_baseline": {
+            "value": value, "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"oracle (NumPy restatement of the reference numpy backend) on {domain} per step; "
+                      f"gt:cpu_* backends not buildable offline (no gridtools-cpp headers)",
+        },
+        "e2e": {"value": value, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---- clocks sampling ---------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5,
+                ).stdout.strip().splitlines()
+                if out:
+                    self.samples.append([x.strip() for x in out[0].split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons,
+            "samples": len(self.samples),
+        }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strategy", default="auto")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    from gt4py_b200 import runtime, storage, testing
+    from gt4py_b200.distributed import HaloExchanger, SlabDecomposition
+    from gt4py_b200.stencil import B200Stencil
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    st_ir = testing.load_ir(STENCIL, VARIANT)
+    stencil = B200Stencil(st_ir, {"strategy": args.strategy, "device_sync": False})
+    shape = (NI + 2 * HALO, NJ + 2 * HALO, NK)
+    origin3 = (HALO, HALO, 0)
+    origins = {"in_field": origin3, "out_field": origin3, "coeff": origin3}
+    domain = (NI, NJ, NK)
+    rng = np.random.default_rng(rank)
+    # two buffer sets, rotated every step (working set 2 x 1 GB >> 126 MB L2)
+    sets = []
+    host_in = host_coeff = None
+    for s in range(2):
+        h_in = rng.random(shape, dtype=np.float32)
+        h_co = rng.random(shape, dtype=np.float32) * np.float32(0.1)
+        sets.append(
+            {
+                "in_field": storage.from_array(h_in, aligned_index=origin3),
+                "coeff": storage.from_array(h_co, aligned_index=origin3),
+                "out_field": storage.zeros(shape, np.float32, aligned_index=origin3),
+            }
+        )
+        if s == 0:
+            host_in, host_coeff = h_in, h_co
+    frozen = stencil.freeze(origin=origins, domain=domain)
+
+    exchanger = None
+    if world > 1:
+        decomp = SlabDecomposition(world, rank, NJ * world)
+        exchanger = HaloExchanger(decomp, NJ)
+    lib = runtime.load_library()
+    main_stream = torch.cuda.current_stream().cuda_stream
+    ev_pool = []
+
+    def make_event():
+        import ctypes
+
+        e = ctypes.c_void_p()
+        runtime.check(lib.b200_event_create(ctypes.byref(e)))
+        ev_pool.append(e)
+        return e
+
+    ev_ready, ev_halo = (make_event(), make_event()) if world > 1 else (None, None)
+
+    launches = 0
+
+    def step(i: int) -> int:
+        """one pass of the hot path over this rank's slab"""
+        bufs = sets[i & 1]
+        if exchanger is None:
+            return frozen(**bufs)
+        n = 0
+        if args.no_overlap:
+            runtime.check(lib.b200_event_record(ev_ready, main_stream))
+            runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
+            n += exchanger.exchange([(bufs["in_field"], HALO, HALO)])
+            runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
+            runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
+            return n + frozen(**bufs)
+        # overlap: halo exchange on the comm stream || interior rows on the compute stream
+        runtime.check(lib.b200_event_record(ev_ready, main_stream))
+        runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
+        n += exchanger.exchange([(bufs["in_field"], HALO, HALO)])
+        runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
+        n += frozen(**bufs, subbox=(0, NI, HALO, NJ - HALO))
+        runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
+        n += frozen(**bufs, subbox=(0, NI, 0, HALO))
+        n += frozen(**bufs, subbox=(0, NI, NJ - HALO, NJ))
+        return n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            launches += step(i)
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        # keep the sampler alive long enough for at least a few samples under load
+        if args.steps * 0 + total_ms < 400:
+            t_end = time.perf_counter() + 0.6
+            j = 0
+            while time.perf_counter() < t_end:
+                step(j)
+                j += 1
+            torch.cuda.synchronize()
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    cells_total = NI * NJ * NK * n_gpus
+    value = cells_total / ms_per_step / 1e3  # Mcell/s
+
+    # ---- dominant-kernel launch duration (events around single launches, same stream) -----------
+    kt = []
+    for i in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        frozen(**sets[i & 1])
+        b.record()
+        b.synchronize()
+        kt.append(a.elapsed_time(b))
+    kernel_ms = float(np.mean(kt))
+    peak, peak_src = measured_peaks()
+    achieved = NI * NJ * NK * BYTES_PER_CELL / kernel_ms / 1e6  # GB/s
+    traffic = None
+    tr = ROOT / "profiles" / "hdiff_traffic.json"
+    if tr.exists():
+        try:
+            traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- end-to-end through the public call with host buffers -------------------------------------
+    e2e = None
+    if True:
+        pin_in = torch.from_numpy(host_in).pin_memory()
+        pin_co = torch.from_numpy(host_coeff).pin_memory()
+        pin_out = torch.empty(shape, dtype=torch.float32).pin_memory()
+        stencil_sync = B200Stencil(st_ir, {"strategy": args.strategy, "device_sync": False})
+        d_in, d_co, d_out = sets[0]["in_field"], sets[0]["coeff"], sets[0]["out_field"]
+        ti, tc, to = d_in.torch(), d_co.torch(), d_out.torch()
+
+        def e2e_step():
+            ti.copy_(pin_in, non_blocking=True)
+            tc.copy_(pin_co, non_blocking=True)
+            if exchanger is not None:
+                runtime.check(lib.b200_event_record(ev_ready, main_stream))
+                runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
+                exchanger.exchange([(d_in, HALO, HALO)])
+                runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
+                runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
+            stencil_sync(d_in, d_out, d_co, origin=origins, domain=domain)  # public StencilObject-style call
+            pin_out.copy_(to, non_blocking=True)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        barrier()
+        e2e_ms = a.elapsed_time(b)
+        if dist is not None:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        nb = int(np.prod(shape)) * 4
+        e2e = {
+            "value": round(cells_total / (e2e_ms / e2e_steps) / 1e3, 1),
+            "unit": "Mcell-updates/s",
+            "h2d_bytes_per_step": 2 * nb,
+            "d2h_bytes_per_step": nb,
+            "steps": e2e_steps,
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": round(value, 1),
+            "unit": "Mcell-updates/s",
+            "n_gpus": n_gpus,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 5),
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"horizontal diffusion (lap-of-lap + flux limiter) {NI}x{NJ}x{NK} fp32 per GPU "
+                f"(BASELINE configs[1]), literal_float_precision=32, fields {shape} origin {origin3}",
+                "parallelism": "single GPU" if n_gpus == 1 else f"J-slab decomposition x{n_gpus}, NCCL halo exchange "
+                + ("(no overlap)" if args.no_overlap else "overlapped with interior"),
+                "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
+                "strategy": args.strategy,
+                "kernels": stencil.compiled.kernel_names(),
+            },
+            "gpu_launches": launches,
+            "e2e": e2e,
+            "roofline": {
+                "bound": "hbm",
+                "achieved": round(achieved, 1),
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": traffic,
+                "peak_source": peak_src,
+                "kernel_ms": round(kernel_ms, 5),
+                "algorithmic_bytes_per_launch": NI * NJ * NK * BYTES_PER_CELL,
+            },
+            "clocks": clocks.summary(),
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if exchanger is not None:
+        exchanger.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

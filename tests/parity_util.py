@@ -25,6 +25,8 @@ def compare(name, fname, got, ref):
 
 def run_case(name, variant="default", options=None, domain=None, seed=0, *, to_device=None, check_golden=False):
     st = testing.load_ir(name, variant)
+    if domain is not None:  # respect the stencil's minimum K size (domain_info.min_sequential_axis_size)
+        domain = (domain[0], domain[1], max(domain[2], int(st["domain_info"]["min_k"])))
     fields, params, origins, domain = testing.make_case_data(st, name, domain=domain, seed=seed)
     ref_fields = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
     numpy_oracle.run(st, ref_fields, params, domain, origins)
