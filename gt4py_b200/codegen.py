@@ -332,6 +332,7 @@ class Generator:
         self.kernels: List[dict] = []
         self.steps: List[dict] = []
         self.src: List[str] = []
+        self.live: set = set()  # fields some kernel addresses in global memory
 
     # -- argument block ---------------------------------------------------------------------------
     def args_struct(self) -> str:
@@ -358,6 +359,7 @@ class Generator:
         """sections: [(interval, [he...])]; all fused in one kernel, K from blockIdx.z."""
         name = self._kname("par")
         all_hes = [he for _, hes in sections for he in hes]
+        self.live |= {a["name"] for he in all_hes for a in b2ir.field_accesses(he["body"])}
         eg = ExprGen(self.ft, _written_in(all_hes))
         ext = _union_extent(all_hes)
         bx, by = self.BLOCK_PAR
@@ -385,6 +387,7 @@ class Generator:
         name = self._kname("seq")
         order = loop["order"]
         all_hes = [he for sec in loop["sections"] for he in sec["hes"]]
+        self.live |= {a["name"] for he in all_hes for a in b2ir.field_accesses(he["body"])}
         eg = ExprGen(self.ft, _written_in(all_hes))
         ext = _union_extent(all_hes)
         bx, by = self.BLOCK_SEQ
@@ -460,7 +463,7 @@ class Generator:
                     "itemsize": b2ir.ITEMSIZE[e["dtype"]],
                     "dims": e["dims"],
                     "data_dims": e["data_dims"],
-                    "kind": e["kind"],
+                    "kind": e["kind"] if (e["kind"] == "api" or e["name"] in self.live) else "dead",
                     "extent": e["extent"],
                 }
                 for e in self.ft.entries
@@ -506,7 +509,7 @@ def plan_to_text(plan: Dict[str, Any]) -> str:
         e = f["extent"] or [[0, 0], [0, 0]]
         dd = f["data_dims"] + [1] * (2 - len(f["data_dims"]))
         L.append(
-            f"field {f['name']} {1 if f['kind'] == 'temp' else 0} {f['itemsize']} "
+            f"field {f['name']} { {'api': 0, 'temp': 1, 'dead': 2}[f['kind']] } {f['itemsize']} "
             f"{int(f['dims'][0])} {int(f['dims'][1])} {int(f['dims'][2])} {len(f['data_dims'])} {dd[0]} {dd[1]} "
             f"{e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]}"
         )

@@ -1,0 +1,631 @@
+"""Streaming ("J-march") generator for PARALLEL computation blocks — the fast path of the backend.
+
+Hand-written-style sm_100a kernel template, instantiated per `computation(PARALLEL)` block:
+
+* one thread owns V consecutive I points (16 bytes: 4 x fp32 or 2 x fp64) -> every global access
+  is a coalesced, vectorised LDG.128/STG.128 of an I-contiguous row segment; a warp owns 32*V
+  consecutive I points of one row
+* a warp *marches along J* over TJ output rows of one K level; every multi-stage temporary
+  (`lap`, `flx`, `fly` in horizontal diffusion) and every input field lives in a small per-thread
+  *register window* of rows (software pipeline: stage s works `lag_s` rows behind the newest
+  loaded row), so each input row is read from memory once per tile and J-neighbours are register
+  reuse, never a re-load
+* I-neighbours come from the adjacent lanes with warp shuffles; the warp's first/last lanes are
+  halo lanes (redundant compute instead of shared memory + barriers -> no __syncthreads at all)
+* stages are fused: nothing but the API outputs (and temporaries another kernel needs) is stored
+* masks / ternaries are predicated (straight-line code), exactly like the oracle's `np.where`
+
+No tensor cores: the path is memory-bound point-wise arithmetic (12-16 B per cell, tens of flops).
+The generic point generator (`codegen.py`) remains the fallback for everything outside this
+template (K-sequential loops, while loops, variable K offsets, data dimensions, lower-dim fields).
+
+Semantics: SURVEY.md §9 (numpy backend).  Reference component replaced: the GridTools multistage
+with ij-caches, gtc/gtcpp/gtcpp_codegen.py:227-247.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+from . import codegen as cg, ir as b2ir
+
+CT = b2ir.CTYPE
+
+
+class NotStreamable(Exception):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------------
+# analysis
+# ---------------------------------------------------------------------------------------------------
+class Value:
+    """A row-streamed value: an input field at a K offset, or one version of a field written here."""
+
+    def __init__(self, kind: str, field: str, dtype: str, *, dk: int = 0, ver: int = 0, stage: int = -1):
+        self.kind, self.field, self.dtype, self.dk, self.ver, self.stage = kind, field, dtype, dk, ver, stage
+        self.reads: List[Tuple[int, int, int]] = []  # (consumer stage, di, dj)
+        self.store = False
+        self.lag = 0
+        self.window = 1
+        self.nj = [0, 0]  # needed rows relative to the owned rows
+        self.ni = [0, 0]  # needed columns relative to the owned columns
+
+    @property
+    def cname(self) -> str:
+        base = cg._cname(self.field)
+        return f"in_{base}_k{self.dk + 8}" if self.kind == "in" else f"v_{base}_{self.ver}"
+
+
+class StreamKernel:
+    def __init__(self, gen: "cg.Generator", interval, hes: List[dict], global_fields: set, opts: Dict[str, Any]):
+        self.gen = gen
+        self.ft = gen.ft
+        self.interval = interval
+        self.hes = hes
+        self.global_fields = global_fields  # temporaries that other kernels touch
+        self.opts = opts
+        self.values: List[Value] = []
+        self.vmap: Dict[Tuple, Value] = {}
+        self.cur: Dict[str, Value] = {}
+        self.stage_of_stmt: List = []
+        self.nstages = len(hes)
+
+    # ---- eligibility + value discovery (pass 1) --------------------------------------------------
+    def _decl(self, name: str) -> dict:
+        return self.ft.entries[self.ft.index[name]]
+
+    def _check_field(self, name: str):
+        d = self._decl(name)
+        if not all(d["dims"]) or d["data_dims"]:
+            raise NotStreamable(f"field {name} is not a plain IJK field")
+        if b2ir.ITEMSIZE[d["dtype"]] not in (4, 8):
+            raise NotStreamable(f"field {name}: itemsize")
+
+    def _in_value(self, name: str, dk: int) -> Value:
+        key = ("in", name, dk)
+        if key not in self.vmap:
+            self._check_field(name)
+            v = Value("in", name, self._decl(name)["dtype"], dk=dk)
+            self.vmap[key] = v
+            self.values.append(v)
+        return self.vmap[key]
+
+    def _new_version(self, name: str, stage: int) -> Value:
+        self._check_field(name)
+        n = sum(1 for v in self.values if v.kind == "tmp" and v.field == name)
+        v = Value("tmp", name, self._decl(name)["dtype"], ver=n, stage=stage)
+        self.vmap[("tmp", name, n)] = v
+        self.values.append(v)
+        return v
+
+    def _resolve_read(self, node, stage: int) -> Tuple[Optional[Value], int, int]:
+        off = node["off"]
+        if isinstance(off, dict) or node.get("data_index"):
+            raise NotStreamable("variable/absolute K offset or data index")
+        di, dj, dk = off
+        name = node["name"]
+        if name in self.cur:
+            if dk != 0:
+                raise NotStreamable("K-offset read of a field written in the same block")
+            v = self.cur[name]
+            if v.stage == stage and (di, dj) != (0, 0):
+                raise NotStreamable("offset read of a value written in the same horizontal execution")
+            return v, di, dj
+        d = self._decl(name)
+        if d["kind"] == "temp" and name not in self.global_fields:
+            # kernel-local temporary read before any write: undefined in the oracle (np.empty)
+            return None, di, dj
+        return self._in_value(name, dk), di, dj
+
+    def analyse(self) -> None:
+        self.binding: Dict[int, Tuple[Optional[Value], int, int]] = {}  # id(expr node) -> read
+        self.assign_ver: Dict[int, Tuple[Value, Optional[Value]]] = {}  # id(stmt) -> (new, prev)
+
+        def visit_expr(e, stage):
+            def fn(n):
+                t = n["t"]
+                if t == "field":
+                    v, di, dj = self._resolve_read(n, stage)
+                    self.binding[id(n)] = (v, di, dj)
+                    if v is not None:
+                        v.reads.append((stage, di, dj))
+                elif t == "iter" and n["axis"] not in ("I", "J", "K"):
+                    raise NotStreamable("iterator")
+
+            b2ir.walk_exprs(e, fn)
+
+        def visit_stmts(stmts, stage, masked):
+            for s in stmts:
+                t = s["t"]
+                if t == "assign":
+                    visit_expr(s["right"], stage)
+                    left = s["left"]
+                    if left["t"] == "field":
+                        if isinstance(left["off"], dict) or left.get("data_index") or tuple(left["off"]) != (0, 0, 0):
+                            raise NotStreamable("write with offset / data index")
+                        name = left["name"]
+                        prev = None
+                        if masked:
+                            if name in self.cur:
+                                prev = self.cur[name]
+                                prev.reads.append((stage, 0, 0))
+                            else:
+                                d = self._decl(name)
+                                if d["kind"] == "api" or name in self.global_fields:
+                                    prev = self._in_value(name, 0)
+                                    prev.reads.append((stage, 0, 0))
+                        new = self._new_version(name, stage)
+                        self.assign_ver[id(s)] = (new, prev)
+                        self.cur[name] = new
+                elif t == "mask":
+                    visit_expr(s["mask"], stage)
+                    visit_stmts(s["body"], stage, True)
+                elif t == "hregion":
+                    visit_stmts(s["body"], stage, True)
+                else:
+                    raise NotStreamable(f"statement {t}")
+
+        for si, he in enumerate(self.hes):
+            visit_stmts(he["body"], si, False)
+        # final versions of API fields / global temporaries are stored
+        for name, v in self.cur.items():
+            d = self._decl(name)
+            if d["kind"] == "api" or name in self.global_fields:
+                v.store = True
+        if not any(v.store for v in self.values):
+            raise NotStreamable("block stores nothing")
+        # drop dead values (never read, never stored)? keep: harmless
+        self.written = set(self.cur.keys())
+        self._schedule()
+
+    # ---- lags, windows, needed ranges (pass 2) -----------------------------------------------------
+    def _schedule(self) -> None:
+        n = self.nstages
+        tmps = [v for v in self.values if v.kind == "tmp"]
+        # ASAP lags per stage
+        lag = [0] * n
+        for s in range(n):
+            for v in tmps:
+                for (c, di, dj) in v.reads:
+                    if c == s and v.stage != s:
+                        lag[s] = max(lag[s], lag[v.stage] + dj)
+        # ALAP: push producers as late as their consumers allow
+        for s in reversed(range(n)):
+            cons = [lag[c] - dj for v in tmps if v.stage == s for (c, di, dj) in v.reads if c != s]
+            if cons:
+                lag[s] = max(lag[s], min(cons))
+        # re-validate (ALAP of a later stage cannot break earlier constraints, but be safe)
+        for v in tmps:
+            for (c, di, dj) in v.reads:
+                if c != v.stage and lag[c] < lag[v.stage] + dj:
+                    raise NotStreamable("lag constraints")
+        base = min(lag)
+        self.lag = [x - base for x in lag]
+        # needed row / column ranges relative to the owned outputs, backwards
+        need_j = [[None, None] for _ in range(n)]
+        need_i = [[None, None] for _ in range(n)]
+
+        def widen(r, lo, hi):
+            r[0] = lo if r[0] is None else min(r[0], lo)
+            r[1] = hi if r[1] is None else max(r[1], hi)
+
+        for s in reversed(range(n)):
+            for v in tmps:
+                if v.stage != s:
+                    continue
+                if v.store:
+                    widen(need_j[s], 0, 0)
+                    widen(need_i[s], 0, 0)
+                for (c, di, dj) in v.reads:
+                    if c == s or need_j[c][0] is None:
+                        continue
+                    widen(need_j[s], need_j[c][0] + dj, need_j[c][1] + dj)
+                    widen(need_i[s], need_i[c][0] + di, need_i[c][1] + di)
+        for s in range(n):
+            if need_j[s][0] is None:  # dead stage
+                need_j[s], need_i[s] = [0, 0], [0, 0]
+        self.need_j, self.need_i = need_j, need_i
+        for v in self.values:
+            if v.kind == "tmp":
+                v.lag = self.lag[v.stage]
+                v.nj, v.ni = list(need_j[v.stage]), list(need_i[v.stage])
+                older = [self.lag[c] - dj for (c, di, dj) in v.reads if c != v.stage]
+                v.window = max(1, (max(older) - v.lag + 1) if older else 1)
+            else:
+                if not v.reads:
+                    continue
+                v.lag = min(self.lag[c] - dj for (c, di, dj) in v.reads)
+                v.window = max(self.lag[c] - dj for (c, di, dj) in v.reads) - v.lag + 1
+                v.nj = [min(need_j[c][0] + dj for (c, di, dj) in v.reads), max(need_j[c][1] + dj for (c, di, dj) in v.reads)]
+                v.ni = [min(need_i[c][0] + di for (c, di, dj) in v.reads), max(need_i[c][1] + di for (c, di, dj) in v.reads)]
+        self.values = [v for v in self.values if v.kind == "tmp" or v.reads]
+        # vector width: 16 bytes of the narrowest streamed field
+        sizes = [b2ir.ITEMSIZE[v.dtype] for v in self.values if v.kind == "in" or v.store]
+        if len(set(sizes)) != 1:
+            raise NotStreamable("mixed item sizes among streamed API fields")
+        self.V = 4 if min(sizes) == 4 else 2
+        V = self.V
+        for v in self.values:
+            for (c, di, dj) in v.reads:
+                if abs(di) > V:
+                    raise NotStreamable("I offset larger than the vector width")
+        ins = [v for v in self.values if v.kind == "in"]
+        lreach = max([0] + [-v.ni[0] for v in ins])
+        rreach = max([0] + [v.ni[1] for v in ins])
+        self.hl, self.hr = math.ceil(lreach / V), math.ceil(rreach / V)
+        self.SQ = 32 - self.hl - self.hr
+        self.U = 1
+        for v in self.values:
+            self.U = self.U * v.window // math.gcd(self.U, v.window)
+        if self.U > 12:
+            raise NotStreamable("window rotation period too long")
+        self.TJ = int(self.opts.get("tile_j", 32))
+        self.NW = int(self.opts.get("warps", 4))
+
+    def declared_extent(self, name: str) -> List[List[int]]:
+        """Authoritative halo of a field = what validation / scratch allocation guarantee to exist:
+        API field -> boundary from field_info; temporary -> its extent."""
+        d = self._decl(name)
+        if d["kind"] == "temp":
+            return d["extent"]
+        b = self.gen.st["field_info"][name]["boundary"]
+        return [[-b[0][0], b[0][1]], [-b[1][0], b[1][1]]]
+
+    # ---- emission (pass 3) ----------------------------------------------------------------------------
+    def reg(self, v: Value, slot: int, e: int) -> str:
+        return f"{v.cname}_s{slot}_{e}"
+
+    def emit(self) -> int:
+        gen, V, U = self.gen, self.V, self.U
+        name = gen._kname("stream")
+        A = "A"
+        L: List[str] = []
+        w = L.append
+        nthreads = 32 * self.NW
+        minb = int(self.opts.get("min_blocks", 0))
+        lb = f"__launch_bounds__({nthreads}, {minb})" if minb else f"__launch_bounds__({nthreads})"
+        w(f'extern "C" __global__ void {lb} {name}(const __grid_constant__ Args A) {{')
+        w(f"  constexpr int V = {V}, SQ = {self.SQ}, HL = {self.hl}, TJ = {self.TJ}, NW = {self.NW};")
+        w("  const int lane = threadIdx.x;")
+        # owned output box of this launch: union of the storing stages' extents
+        st_stages = sorted({v.stage for v in self.values if v.store})
+        ei0 = min(self.hes[s]["extent"][0][0] for s in st_stages)
+        ei1 = max(self.hes[s]["extent"][0][1] for s in st_stages)
+        ej0 = min(self.hes[s]["extent"][1][0] for s in st_stages)
+        ej1 = max(self.hes[s]["extent"][1][1] for s in st_stages)
+        self.store_ext = [[ei0, ei1], [ej0, ej1]]
+        w(f"  const int X0 = {A}.g.i_lo + ({ei0}), X1 = {A}.g.i_hi + ({ei1});")
+        w(f"  const int Y0 = {A}.g.j_lo + ({ej0}), Y1 = {A}.g.j_hi + ({ej1});")
+        w("  const int QX0 = (X0 >= 0) ? X0 / V : -((-X0 + V - 1) / V);")
+        w("  const int nseg = ((X1 - QX0 * V) + SQ * V - 1) / (SQ * V);")
+        w("  const int ntj = (Y1 - Y0 + TJ - 1) / TJ;")
+        w("  const long long task = (long long)blockIdx.x * NW + threadIdx.y;")
+        w(f"  const int nk = {A}.g.k_hi - {A}.g.k_lo;")
+        w("  if (task >= (long long)nseg * ntj * nk) return;")
+        w("  const int seg = (int)(task % nseg);")
+        w("  const int tj = (int)((task / nseg) % ntj);")
+        w(f"  const int k = {A}.g.k_lo + (int)(task / ((long long)nseg * ntj));")
+        k0 = cg._bound(self.interval[0], f"{A}.g.nK")
+        k1 = cg._bound(self.interval[1], f"{A}.g.nK")
+        w(f"  if (k < {k0} || k >= {k1}) return;")
+        w("  const int g0 = (QX0 + seg * SQ - HL + lane) * V;   // first I index of this lane's vector")
+        w("  const bool own = (lane >= HL) && (lane < HL + SQ);")
+        w("  const int T_lo = Y0 + tj * TJ;")
+        w("  const int T_hi = (T_lo + TJ < Y1) ? T_lo + TJ : Y1;")
+        # per-element global-validity predicates are computed per value (ranges differ)
+        for v in self.values:
+            ct = CT[v.dtype]
+            for s in range(v.window):
+                w("  " + f"{ct} " + ", ".join(f"{self.reg(v, s, e)} = ({ct})0" for e in range(V)) + ";")
+        for v in self.values:
+            if v.kind == "in" or v.store:
+                n = self.ft.index[v.field]
+                ct = CT[v.dtype]
+                w(f"  const {ct}* const p_{v.cname} = (const {ct}*){A}.f[{n}].p + (long long)(k + ({v.dk})) * {A}.f[{n}].s[2];"
+                  if v.kind == "in" else
+                  f"  {ct}* const p_{v.cname} = ({ct}*){A}.f[{n}].p + (long long)k * {A}.f[{n}].s[2];")
+                w(f"  const bool vec_{v.cname} = {A}.f[{n}].vec != 0;")
+                w(f"  const long long sj_{v.cname} = {A}.f[{n}].s[1], si_{v.cname} = {A}.f[{n}].s[0];")
+                if v.kind == "in":
+                    de = self.declared_extent(v.field)
+                    lo = f"{A}.g.i_lo + ({max(ei0 + v.ni[0], de[0][0])})"
+                    hi = f"{A}.g.i_hi + ({min(ei1 + v.ni[1], de[0][1])})"
+                    w(f"  const int rlo_{v.cname} = {A}.g.j_lo + ({de[1][0]}), rhi_{v.cname} = {A}.g.j_hi + ({de[1][1]});")
+                else:
+                    e = self.hes[v.stage]["extent"]
+                    lo = f"{A}.g.i_lo + ({e[0][0]})"
+                    hi = f"{A}.g.i_hi + ({e[0][1]})"
+                w(f"  const int clo_{v.cname} = {lo}, chi_{v.cname} = {hi};")
+                w(f"  const bool full_{v.cname} = vec_{v.cname} && g0 >= clo_{v.cname} && g0 + V <= chi_{v.cname};")
+                w(f"  const bool any_{v.cname} = g0 + V > clo_{v.cname} && g0 < chi_{v.cname};")
+        lag_terms = [self.need_j[s][0] + self.lag[s] for s in range(self.nstages)] + [
+            v.nj[0] + v.lag for v in self.values if v.kind == "in"
+        ]
+        last_terms = [self.need_j[s][1] + self.lag[s] for s in range(self.nstages)]
+        t_first, t_last = min(lag_terms), max(last_terms)
+        w(f"  const int t_begin = T_lo + ({t_first});")
+        w(f"  const int t_end = T_hi + ({t_last});   // exclusive")
+        w(f"  for (int t = t_begin; t < t_end; t += {U}) {{")
+        for phase in range(U):
+            w(f"    {{  // rotation phase {phase}")
+            w(f"      const int tt = t + {phase};")
+            L.extend(self._emit_step(phase))
+            w("    }")
+        w("  }")
+        w("}")
+        gen.src.append("\n".join(L))
+        gen.live |= {v.field for v in self.values if v.kind == "in" or v.store}
+        gen.kernels.append(
+            {
+                "name": name, "kind": "stream", "block": [32, self.NW, 1], "tile": [self.SQ * V, self.TJ, V],
+                "extent": self.store_ext, "k_lo": self.interval[0], "k_hi": self.interval[1], "smem": 0,
+                "vector": V,
+            }
+        )  # fmt: skip
+        return len(gen.kernels) - 1
+
+    # one march step at rotation phase `phase`
+    def _emit_step(self, phase: int) -> List[str]:
+        V = self.V
+        L: List[str] = []
+        ind = "      "
+        # 1. loads of the newest row of every input stream
+        for v in self.values:
+            if v.kind != "in":
+                continue
+            slot = phase % v.window
+            c = v.cname
+            row = f"(tt - ({v.lag}))"
+            L.append(f"{ind}{{ const int R = {row};")
+            L.append(f"{ind}  if (R >= T_lo + ({v.nj[0]}) && R < T_hi + ({v.nj[1]}) && R >= rlo_{c} && R < rhi_{c} && any_{c}) {{")
+            ct = CT[v.dtype]
+            regs = [self.reg(v, slot, e) for e in range(V)]
+            L.append(f"{ind}    const {ct}* q = p_{c} + (long long)R * sj_{c};")
+            L.append(f"{ind}    if (full_{c}) {{")
+            ro = v.field not in self.written
+            L.append(f"{ind}      {_vec_load(ct, V, regs, 'q + g0', ro)}")
+            L.append(f"{ind}    }} else {{")
+            for e in range(V):
+                L.append(
+                    f"{ind}      if (g0 + {e} >= clo_{c} && g0 + {e} < chi_{c}) {regs[e]} = {'__ldg' if ro else '*'}(q + (long long)(g0 + {e}) * si_{c});"
+                )
+            L.append(f"{ind}    }}")
+            L.append(f"{ind}  }}")
+            L.append(f"{ind}}}")
+        # 2. stages
+        for si, he in enumerate(self.hes):
+            L.extend(self._emit_stage(si, he, phase))
+        return L
+
+    def _slot_of(self, v: Value, consumer_lag: int, dj: int, phase: int) -> int:
+        m = consumer_lag - dj - v.lag  # rows behind the newest row of v
+        assert 0 <= m < v.window, (v.cname, m, v.window)
+        return (phase - m) % v.window
+
+    def _emit_stage(self, si: int, he: dict, phase: int) -> List[str]:
+        V = self.V
+        ind = "      "
+        L: List[str] = [f"{ind}{{  // stage {si}, row r = tt - {self.lag[si]}"]
+        ind2 = ind + "  "
+        L.append(f"{ind2}const int r = tt - ({self.lag[si]});")
+        shuf_defined: set = set()
+        mask_counter = [0]
+        kern = self
+
+        class EG(cg.ExprGen):
+            def __init__(self, elem):
+                super().__init__(kern.ft, set(), args="A")
+                self.elem = elem
+                self.pre: List[str] = []
+                self.k = "k"
+                self.i = f"(g0 + {elem})"
+                self.j = "r"
+
+            def field_load(self, node):
+                v, di, dj = kern.binding[id(node)]
+                if v is None:
+                    return f"(({CT[node['dtype']]})0)"
+                slot = kern._slot_of(v, kern.lag[si], dj, phase)
+                e = self.elem + di
+                if 0 <= e < V:
+                    return kern.reg(v, slot, e)
+                if e < 0:
+                    src, delta, fn, tag = e + V, 1, "__shfl_up_sync", "L"
+                else:
+                    src, delta, fn, tag = e - V, 1, "__shfl_down_sync", "R"
+                nm = f"{kern.reg(v, slot, src)}_{tag}"
+                if nm not in shuf_defined:
+                    shuf_defined.add(nm)
+                    self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, {delta});")
+                return nm
+
+            def expr(self, n):
+                if n["t"] == "scalar" and n["name"] in self.locals:
+                    return f"{self.locals[n['name']]}_{self.elem}"
+                return super().expr(n)
+
+        egs = [EG(e) for e in range(V)]
+        for d in he["locals"]:
+            for eg in egs:
+                eg.locals[d["name"]] = f"l_{d['name']}"
+            ct = CT[d["dtype"]]
+            L.append(ind2 + f"{ct} " + ", ".join(f"l_{d['name']}_{e} = ({ct})0" for e in range(V)) + ";")
+
+        def flush_pre():
+            for eg in egs:
+                for line in eg.pre:
+                    L.append(ind2 + line)
+                eg.pre = []
+
+        def emit_stmts(stmts, masks: List[Optional[str]]):
+            # masks: per-element condition variable names (None = unconditional)
+            for s in stmts:
+                t = s["t"]
+                if t == "assign":
+                    rhs = [egs[e].expr(s["right"]) for e in range(V)]
+                    flush_pre()
+                    left = s["left"]
+                    if left["t"] == "scalar":
+                        ct = CT[left["dtype"]]
+                        for e in range(V):
+                            tgt = f"l_{left['name']}_{e}"
+                            val = f"({ct})({rhs[e]})"
+                            L.append(ind2 + (f"{tgt} = {masks[e]} ? {val} : {tgt};" if masks[e] else f"{tgt} = {val};"))
+                    else:
+                        new, prev = kern.assign_ver[id(s)]
+                        ct = CT[new.dtype]
+                        slot = phase % new.window
+                        for e in range(V):
+                            tgt = kern.reg(new, slot, e)
+                            val = f"({ct})({rhs[e]})"
+                            if masks[e]:
+                                if prev is None:
+                                    old = f"({ct})0"
+                                else:
+                                    old = kern.reg(prev, kern._slot_of(prev, kern.lag[si], 0, phase), e)
+                                L.append(ind2 + f"{tgt} = {masks[e]} ? {val} : {old};")
+                            else:
+                                L.append(ind2 + f"{tgt} = {val};")
+                        if new.store:
+                            L.extend(kern._emit_store(new, slot, ind2))
+                elif t == "mask":
+                    conds = [egs[e].expr(s["mask"]) for e in range(V)]
+                    flush_pre()
+                    mid = mask_counter[0]
+                    mask_counter[0] += 1
+                    names = []
+                    for e in range(V):
+                        nm = f"m{mid}_{e}"
+                        c = f"({conds[e]})" + (f" && {masks[e]}" if masks[e] else "")
+                        L.append(ind2 + f"const bool {nm} = {c};")
+                        names.append(nm)
+                    emit_stmts(s["body"], names)
+                elif t == "hregion":
+                    mid = mask_counter[0]
+                    mask_counter[0] += 1
+                    names = []
+                    for e in range(V):
+                        conds = []
+                        for var, n_sym, (lo, hi) in ((f"(g0 + {e})", "A.g.nI", s["i"]), ("r", "A.g.nJ", s["j"])):
+                            if lo is not None:
+                                conds.append(f"{var} >= {cg._bound(lo, n_sym)}")
+                            if hi is not None:
+                                conds.append(f"{var} < {cg._bound(hi, n_sym)}")
+                        if masks[e]:
+                            conds.append(masks[e])
+                        nm = f"m{mid}_{e}"
+                        L.append(ind2 + f"const bool {nm} = {' && '.join(conds) if conds else 'true'};")
+                        names.append(nm)
+                    emit_stmts(s["body"], names)
+                else:  # pragma: no cover
+                    raise NotStreamable(t)
+
+        emit_stmts(he["body"], [None] * V)
+        L.append(f"{ind}}}")
+        return L
+
+    def _emit_store(self, v: Value, slot: int, ind: str) -> List[str]:
+        V = self.V
+        c = v.cname
+        e = self.hes[v.stage]["extent"]
+        regs = [self.reg(v, slot, x) for x in range(V)]
+        ct = CT[v.dtype]
+        L = [
+            f"{ind}if (own && r >= T_lo && r < T_hi && r >= A.g.j_lo + ({e[1][0]}) && r < A.g.j_hi + ({e[1][1]}) && any_{c}) {{",
+            f"{ind}  {ct}* q = p_{c} + (long long)r * sj_{c};",
+            f"{ind}  if (full_{c}) {{",
+            f"{ind}    {_vec_store(ct, V, regs, 'q + g0')}",
+            f"{ind}  }} else {{",
+        ]
+        for x in range(V):
+            L.append(f"{ind}    if (g0 + {x} >= clo_{c} && g0 + {x} < chi_{c}) q[(long long)(g0 + {x}) * si_{c}] = {regs[x]};")
+        L += [f"{ind}  }}", f"{ind}}}"]
+        return L
+
+
+def _vec_type(ct: str, V: int) -> Tuple[str, List[str]]:
+    size = {"float": 4, "int": 4, "double": 8, "long long": 8}[ct] * V
+    if size == 16:
+        return "int4", ["x", "y", "z", "w"]
+    if size == 8:
+        return "int2", ["x", "y"]
+    raise NotStreamable("vector size")
+
+
+def _vec_load(ct: str, V: int, regs: List[str], addr: str, ro: bool = True) -> str:
+    """16-byte load into V scalar registers (bit casts keep any 4/8-byte element type);
+    `ro`: the field is never written by this kernel -> read-only (non-coherent) path."""
+    ld = "__ldg" if ro else "*"
+    if ct in ("float", "int"):
+        cast = "__int_as_float" if ct == "float" else ""
+        comps = ["x", "y", "z", "w"][:V]
+        body = " ".join(f"{regs[e]} = {cast}(u.{comps[e]});" for e in range(V))
+        vt = "int4" if V == 4 else "int2"
+        return f"{{ const {vt} u = {ld}(reinterpret_cast<const {vt}*>({addr})); {body} }}"
+    # 8-byte elements, V == 2
+    if ct == "double":
+        return (
+            f"{{ const int4 u = {ld}(reinterpret_cast<const int4*>({addr})); "
+            f"{regs[0]} = __hiloint2double(u.y, u.x); {regs[1]} = __hiloint2double(u.w, u.z); }}"
+        )
+    return (
+        f"{{ const longlong2 u = {ld}(reinterpret_cast<const longlong2*>({addr})); {regs[0]} = u.x; {regs[1]} = u.y; }}"
+    )
+
+
+def _vec_store(ct: str, V: int, regs: List[str], addr: str) -> str:
+    if ct == "float":
+        vt = "float4" if V == 4 else "float2"
+        return f"*reinterpret_cast<{vt}*>({addr}) = make_{vt}({', '.join(regs)});"
+    if ct == "int":
+        vt = "int4" if V == 4 else "int2"
+        return f"*reinterpret_cast<{vt}*>({addr}) = make_{vt}({', '.join(regs)});"
+    if ct == "double":
+        return f"*reinterpret_cast<double2*>({addr}) = make_double2({regs[0]}, {regs[1]});"
+    return f"*reinterpret_cast<longlong2*>({addr}) = make_longlong2({regs[0]}, {regs[1]});"
+
+
+# ---------------------------------------------------------------------------------------------------
+# driver
+# ---------------------------------------------------------------------------------------------------
+def _fields_touched(hes) -> set:
+    return {a["name"] for he in hes for a in b2ir.field_accesses(he["body"])}
+
+
+def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
+    """Generate with streaming kernels for every PARALLEL section that fits the template; other
+    loops use the point generator.  Returns None when nothing is streamable."""
+    gen = cg.Generator(stencil, options)
+    used_stream = False
+    # fields touched per (loop, section) to decide which temporaries are kernel-local
+    secs = [(li, si) for li, loop in enumerate(stencil["loops"]) for si, _ in enumerate(loop["sections"])]
+    touched = {(li, si): _fields_touched(stencil["loops"][li]["sections"][si]["hes"]) for li, si in secs}
+    temps = {t["name"] for t in stencil["temporaries"]}
+    for li, loop in enumerate(stencil["loops"]):
+        if loop["order"] != "parallel":
+            gen.lower_loop(loop)
+            continue
+        plans = []
+        ok = True
+        for si, sec in enumerate(loop["sections"]):
+            others = set().union(*[f for key, f in touched.items() if key != (li, si)]) if len(touched) > 1 else set()
+            global_fields = temps & others
+            sk = StreamKernel(gen, sec["interval"], sec["hes"], global_fields, options)
+            try:
+                sk.analyse()
+            except NotStreamable:
+                ok = False
+                break
+            plans.append(sk)
+        if not ok:
+            gen.lower_loop(loop)
+            continue
+        for sk in plans:
+            k = sk.emit()
+            gen.steps.append({"t": "launch", "kernel": k})
+            used_stream = True
+    if not used_stream:
+        return None
+    return gen.finish()

@@ -14,10 +14,12 @@ namespace b200 {
 //   s[3..4]: element strides of up to two data dimensions
 //   klo/khi: valid K index range relative to the origin (for clipping variable-K accesses,
 //            reference: cartesian/utils/field.py:54-58)
+//   vec    : 1 when I is unit-stride and origin / J / K strides are 16-byte aligned (vector path)
 struct FieldArg {
   char* p;
   long long s[5];
   int klo, khi;
+  int vec, _pad;
 };
 
 // Launch geometry common to all kernels of a stencil call.

@@ -49,6 +49,7 @@ struct FieldArg {
   char* p;
   long long s[5];
   int klo, khi;
+  int vec, _pad;
 };
 struct Geom {
   int nI, nJ, nK;
@@ -56,7 +57,7 @@ struct Geom {
   int k_lo, k_hi;
   int _pad;
 };
-static_assert(sizeof(FieldArg) == 56, "FieldArg layout");
+static_assert(sizeof(FieldArg) == 64, "FieldArg layout");
 static_assert(sizeof(Geom) == 40, "Geom layout");
 
 struct Bound {
@@ -218,6 +219,14 @@ TempLayout temp_layout(const FieldPlan& f, const int32_t dom[3], size_t offset) 
   return t;
 }
 
+// vector (16-byte) path is legal when I is unit-stride and every row start is 16-byte aligned
+int vec_ok(const FieldArg& a, int itemsize) {
+  if (a.s[0] != 1) return 0;
+  if (((uintptr_t)a.p) & 15) return 0;
+  if (((a.s[1] * itemsize) & 15) || ((a.s[2] * itemsize) & 15)) return 0;
+  return 1;
+}
+
 int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, int k_hi, cudaStream_t stream) {
   Geom* g = reinterpret_cast<Geom*>(blob.data());
   int nx = (g->i_hi + k.ei1) - (g->i_lo + k.ei0);
@@ -228,6 +237,18 @@ int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, i
   g->k_hi = k_hi;
   dim3 grid((nx + k.tile[0] - 1) / k.tile[0], (ny + k.tile[1] - 1) / k.tile[1], (nz + k.tile[2] - 1) / k.tile[2]);
   dim3 block(k.block[0], k.block[1], k.block[2]);
+  if (k.kind == 2) {
+    // streaming kernels: one warp per (I segment, J tile, K level) task, block[1] warps per CTA;
+    // tile = {I points per segment, rows per tile, vector width}; segments start at the vector-aligned
+    // column at or below the first stored column (must match codegen_stream.py)
+    const int V = k.tile[2];
+    const int x0 = g->i_lo + k.ei0, x1 = g->i_hi + k.ei1;
+    const int qx0 = x0 >= 0 ? x0 / V : -((-x0 + V - 1) / V);
+    const long long nseg = ((x1 - qx0 * V) + k.tile[0] - 1) / k.tile[0];
+    const long long ntj = (ny + k.tile[1] - 1) / k.tile[1];
+    const long long tasks = nseg * ntj * nz;
+    grid = dim3((unsigned)((tasks + k.block[1] - 1) / k.block[1]), 1, 1);
+  }
   if (grid.y > 65535 || grid.z > 65535) return fail(B200_ERR_INVALID, "grid too large for kernel %s", k.name.c_str());
   void* params[1] = {blob.data()};
   CU(cudaLaunchKernel((const void*)k.fn, grid, block, params, (size_t)k.smem, stream));
@@ -321,7 +342,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
   std::vector<TempLayout> tl(nf);
   size_t need = 0;
   for (size_t n = 0; n < nf; ++n)
-    if (st->fields[n].is_temp) {
+    if (st->fields[n].is_temp == 1) {
       tl[n] = temp_layout(st->fields[n], domain, need);
       need += tl[n].bytes;
     }
@@ -353,6 +374,10 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
   for (size_t n = 0; n < nf; ++n) {
     const FieldPlan& fp = st->fields[n];
     FieldArg& a = fa[n];
+    if (fp.is_temp == 2) {  // temporary that lives entirely in registers: no scratch
+      a.p = nullptr;
+      continue;
+    }
     if (fp.is_temp) {
       const TempLayout& t = tl[n];
       for (int d = 0; d < 5; ++d) a.s[d] = t.s[d];
@@ -360,6 +385,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       a.p = (char*)st->scratch + t.offset + off * fp.itemsize;
       a.klo = 0;
       a.khi = t.shape[2];
+      a.vec = vec_ok(a, fp.itemsize);
     } else {
       const b200_field_t& f = fields[api++];
       if (!f.data) {  // unreferenced argument (AccessKind.NONE)
@@ -373,6 +399,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       a.p = (char*)f.data + off * fp.itemsize;
       a.klo = fp.dims[2] ? -f.origin[2] : 0;
       a.khi = fp.dims[2] ? f.shape[2] - f.origin[2] : 1;
+      a.vec = vec_ok(a, fp.itemsize);
     }
   }
   if (st->scalars_size) memcpy(blob.data() + scal_off, scalars, st->scalars_size);

@@ -28,15 +28,28 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); a = ap.parse_args()
     runs = [
         ("hdiff_f32","default","point",(1024,1024,80)),
-        ("hdiff_f32","staged","point",(1024,1024,80)),
         ("hdiff_f32","staged","auto",(1024,1024,80)),
-        ("copy_f64","default","point",(1024,1024,40)),
-        ("laplacian_f64","default","point",(1024,1024,40)),
-        ("tridiagonal_f64","default","point",(512,512,160)),
-        ("vadv_f64","default","point",(512,512,80)),
-        ("upwind5_f32","default","point",(2048,2048,20)),
+        ("hdiff_f32","default","auto",(1024,1024,80)),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":16}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":64}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":128}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"warps":2}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"warps":8}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":64,"warps":8}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"min_blocks":4}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"min_blocks":6,"tile_j":64}),
+        ("hdiff_f32","staged","auto",(1024,1024,80), {"fmad":True}),
+        ("hdiff_f32_default_literals","staged","auto",(1024,1024,80)),
+        ("copy_f64","default","auto",(1024,1024,40)),
+        ("laplacian_f64","default","auto",(1024,1024,40)),
+        ("upwind5_f32","default","auto",(2048,2048,20)),
         ("upwind5_f32","staged","auto",(2048,2048,20)),
+        ("fw_pgrad_f32","staged","auto",(1024,1024,40)),
+        ("fw_div_f32","staged","auto",(1024,1024,40)),
+        ("tridiagonal_f64","default","point",(512,512,160)),
     ]
     for r in runs:
-        try: print(json.dumps(bench(*r)), flush=True)
+        try:
+            extra = r[4] if len(r) > 4 else None
+            print(json.dumps(bench(*r[:4], extra=extra)), flush=True)
         except Exception as e: print("FAIL", r, repr(e)[:500], flush=True)
