@@ -256,13 +256,42 @@ class StreamKernel:
         rreach = max([0] + [v.ni[1] for v in ins])
         self.hl, self.hr = math.ceil(lreach / V), math.ceil(rreach / V)
         self.SQ = 32 - self.hl - self.hr
-        self.U = 1
-        for v in self.values:
-            self.U = self.U * v.window // math.gcd(self.U, v.window)
-        if self.U > 12:
-            raise NotStreamable("window rotation period too long")
+        self._choose_windows()
         self.TJ = int(self.opts.get("tile_j", 32))
         self.NW = int(self.opts.get("warps", 4))
+
+    def _choose_windows(self) -> None:
+        """Pick the rotation period U and the final register-window sizes.
+
+        Inputs get `prefetch` extra rows (loads issued that many march steps before first use ->
+        more bytes in flight per warp).  A window that divides U rotates by register renaming in the
+        U-times unrolled march loop (no moves); the others shift (W-1 moves per element and step)."""
+        pf = int(self.opts.get("prefetch", 1))
+        req = {}
+        for v in self.values:
+            req[id(v)] = v.window + (pf if v.kind == "in" else 0)
+        best = None
+        for P in (1, 2, 3, 4, 6):
+            divs = [d for d in range(1, P + 1) if P % d == 0]
+            cost, assign = 0, {}
+            for v in self.values:
+                r = req[id(v)]
+                fit = [d for d in divs if d >= r]
+                if fit:
+                    assign[id(v)] = (fit[0], False)
+                    cost += fit[0]
+                else:
+                    assign[id(v)] = (r, True)
+                    cost += 3 * r
+            cost += 0.25 * P  # code size
+            if best is None or cost < best[0]:
+                best = (cost, P, assign)
+        _, self.U, assign = best
+        for v in self.values:
+            w, shift = assign[id(v)]
+            if v.kind == "in":
+                v.lag -= w - v.window  # loads run ahead of first use
+            v.window, v.shift = w, shift
 
     def declared_extent(self, name: str) -> List[List[int]]:
         """Authoritative halo of a field = what validation / scratch allocation guarantee to exist:
@@ -276,6 +305,14 @@ class StreamKernel:
     # ---- emission (pass 3) ----------------------------------------------------------------------------
     def reg(self, v: Value, slot: int, e: int) -> str:
         return f"{v.cname}_s{slot}_{e}"
+
+    def _slot_of(self, v: Value, consumer_lag: int, dj: int, phase: int) -> int:
+        m = consumer_lag - dj - v.lag  # rows behind the newest row of v
+        assert 0 <= m < v.window, (v.cname, m, v.window)
+        return m if v.shift else (phase - m) % v.window
+
+    def _new_slot(self, v: Value, phase: int) -> int:
+        return 0 if v.shift else phase % v.window
 
     def emit(self) -> int:
         gen, V, U = self.gen, self.V, self.U
@@ -314,11 +351,11 @@ class StreamKernel:
         w("  const bool own = (lane >= HL) && (lane < HL + SQ);")
         w("  const int T_lo = Y0 + tj * TJ;")
         w("  const int T_hi = (T_lo + TJ < Y1) ? T_lo + TJ : Y1;")
-        # per-element global-validity predicates are computed per value (ranges differ)
         for v in self.values:
             ct = CT[v.dtype]
             for s in range(v.window):
                 w("  " + f"{ct} " + ", ".join(f"{self.reg(v, s, e)} = ({ct})0" for e in range(V)) + ";")
+        self.row_guard: Dict[str, bool] = {}
         for v in self.values:
             if v.kind == "in" or v.store:
                 n = self.ft.index[v.field]
@@ -333,25 +370,64 @@ class StreamKernel:
                     lo = f"{A}.g.i_lo + ({max(ei0 + v.ni[0], de[0][0])})"
                     hi = f"{A}.g.i_hi + ({min(ei1 + v.ni[1], de[0][1])})"
                     w(f"  const int rlo_{v.cname} = {A}.g.j_lo + ({de[1][0]}), rhi_{v.cname} = {A}.g.j_hi + ({de[1][1]});")
+                    # rows the tile needs may exceed what is declared valid only if the need analysis is
+                    # coarser than the extent analysis; then the steady loop keeps the row guard
+                    self.row_guard[v.cname] = not (ej0 + v.nj[0] >= de[1][0] and ej1 + v.nj[1] <= de[1][1])
                 else:
                     e = self.hes[v.stage]["extent"]
                     lo = f"{A}.g.i_lo + ({e[0][0]})"
                     hi = f"{A}.g.i_hi + ({e[0][1]})"
+                    self.row_guard[v.cname] = not (e[1][0] == ej0 and e[1][1] == ej1)
                 w(f"  const int clo_{v.cname} = {lo}, chi_{v.cname} = {hi};")
                 w(f"  const bool full_{v.cname} = vec_{v.cname} && g0 >= clo_{v.cname} && g0 + V <= chi_{v.cname};")
                 w(f"  const bool any_{v.cname} = g0 + V > clo_{v.cname} && g0 < chi_{v.cname};")
-        lag_terms = [self.need_j[s][0] + self.lag[s] for s in range(self.nstages)] + [
+                # branch-free handling of partially valid vectors in the steady loop (unit I stride)
+                gate = "" if v.kind == "in" else "own && "
+                for e in range(V):
+                    w(f"  const bool pe_{v.cname}_{e} = {gate}vec_{v.cname} && !full_{v.cname} && g0 + {e} >= clo_{v.cname} && g0 + {e} < chi_{v.cname};")
+                if v.kind != "in":
+                    w(f"  const bool sfull_{v.cname} = own && full_{v.cname};")
+        w("  const bool allvec = " + " && ".join(f"vec_{v.cname}" for v in self.values if v.kind == "in" or v.store) + ";")
+        # march ranges (in step space, relative to the tile rows)
+        first_terms = [self.need_j[s][0] + self.lag[s] for s in range(self.nstages)] + [
             v.nj[0] + v.lag for v in self.values if v.kind == "in"
         ]
         last_terms = [self.need_j[s][1] + self.lag[s] for s in range(self.nstages)]
-        t_first, t_last = min(lag_terms), max(last_terms)
-        w(f"  const int t_begin = T_lo + ({t_first});")
+        t_first, t_last = min(first_terms), max(last_terms)
+        # steady state: every load row is inside the tile's needed rows, every store row is owned
+        lo_terms = [v.nj[0] + v.lag for v in self.values if v.kind == "in"] + [v.lag for v in self.values if v.store]
+        hi_terms = [v.nj[1] + v.lag for v in self.values if v.kind == "in"] + [v.lag for v in self.values if v.store]
+        a, b = max(lo_terms), min(hi_terms)
+        n_pro = a - t_first
+        w(f"  int t = T_lo + ({t_first});")
         w(f"  const int t_end = T_hi + ({t_last});   // exclusive")
-        w(f"  for (int t = t_begin; t < t_end; t += {U}) {{")
-        for phase in range(U):
-            w(f"    {{  // rotation phase {phase}")
-            w(f"      const int tt = t + {phase};")
-            L.extend(self._emit_step(phase))
+        # prologue: general steps until the steady state starts (compile-time count)
+        for n in range(n_pro):
+            w(f"  if (t < t_end) {{  // prologue step {n}")
+            w("      const int tt = t;")
+            L.extend(self._emit_step(n % U, fast=False))
+            w("  }")
+            w("  ++t;")
+        ph0 = n_pro % U
+        # steady state: U fast steps per trip, running row pointers
+        for v in self.values:
+            if v.kind == "in" or v.store:
+                ct = CT[v.dtype]
+                const = "const " if v.kind == "in" else ""
+                w(f"  {const}{ct}* q_{v.cname} = p_{v.cname} + (long long)(t - ({v.lag})) * sj_{v.cname} + g0;")
+        w(f"  if (allvec) for (; t + {U} <= T_hi + ({b}); t += {U}) {{")
+        for u in range(U):
+            w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
+            w(f"      const int tt = t + {u};")
+            L.extend(self._emit_step((ph0 + u) % U, fast=True))
+            w("    }")
+        w("  }")
+        # tail: remaining steady rows + epilogue, general steps, same phase sequence
+        w(f"  for (; t < t_end; t += {U}) {{")
+        for u in range(U):
+            w(f"    if (t + {u} < t_end) {{  // tail step, rotation phase {(ph0 + u) % U}")
+            w(f"      const int tt = t + {u};")
+            L.extend(self._emit_step((ph0 + u) % U, fast=False))
             w("    }")
         w("  }")
         w("}")
@@ -361,50 +437,62 @@ class StreamKernel:
             {
                 "name": name, "kind": "stream", "block": [32, self.NW, 1], "tile": [self.SQ * V, self.TJ, V],
                 "extent": self.store_ext, "k_lo": self.interval[0], "k_hi": self.interval[1], "smem": 0,
-                "vector": V,
+                "vector": V, "period": U, "windows": {v.cname: (v.window, "shift" if v.shift else "rot") for v in self.values},
             }
         )  # fmt: skip
         return len(gen.kernels) - 1
 
     # one march step at rotation phase `phase`
-    def _emit_step(self, phase: int) -> List[str]:
+    def _emit_step(self, phase: int, fast: bool) -> List[str]:
         V = self.V
         L: List[str] = []
         ind = "      "
+        # 0. shifting windows (values whose window does not divide the rotation period)
+        for v in self.values:
+            if v.shift and v.window > 1:
+                for s in range(v.window - 1, 0, -1):
+                    L.append(ind + " ".join(f"{self.reg(v, s, e)} = {self.reg(v, s - 1, e)};" for e in range(V)))
         # 1. loads of the newest row of every input stream
         for v in self.values:
             if v.kind != "in":
                 continue
-            slot = phase % v.window
+            slot = self._new_slot(v, phase)
             c = v.cname
-            row = f"(tt - ({v.lag}))"
-            L.append(f"{ind}{{ const int R = {row};")
-            L.append(f"{ind}  if (R >= T_lo + ({v.nj[0]}) && R < T_hi + ({v.nj[1]}) && R >= rlo_{c} && R < rhi_{c} && any_{c}) {{")
             ct = CT[v.dtype]
+            ro = v.field not in self.written
             regs = [self.reg(v, slot, e) for e in range(V)]
+            ldf = "__ldg" if ro else "*"
+            if fast:
+                guard = f"R >= rlo_{c} && R < rhi_{c}" if self.row_guard[c] else ""
+                L.append(f"{ind}{{")
+                if guard:
+                    L.append(f"{ind}  const int R = tt - ({v.lag}); const bool rok = {guard};")
+                g = "rok && " if guard else ""
+                L.append(f"{ind}  if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                for e in range(V):
+                    L.append(f"{ind}  if ({g}pe_{c}_{e}) {regs[e]} = {ldf}(q_{c} + {e});")
+                L.append(f"{ind}  q_{c} += sj_{c};")
+                L.append(f"{ind}}}")
+                continue
+            L.append(f"{ind}{{ const int R = tt - ({v.lag});")
+            L.append(f"{ind}  if (R >= T_lo + ({v.nj[0]}) && R < T_hi + ({v.nj[1]}) && R >= rlo_{c} && R < rhi_{c} && any_{c}) {{")
             L.append(f"{ind}    const {ct}* q = p_{c} + (long long)R * sj_{c};")
             L.append(f"{ind}    if (full_{c}) {{")
-            ro = v.field not in self.written
             L.append(f"{ind}      {_vec_load(ct, V, regs, 'q + g0', ro)}")
             L.append(f"{ind}    }} else {{")
             for e in range(V):
                 L.append(
-                    f"{ind}      if (g0 + {e} >= clo_{c} && g0 + {e} < chi_{c}) {regs[e]} = {'__ldg' if ro else '*'}(q + (long long)(g0 + {e}) * si_{c});"
+                    f"{ind}      if (g0 + {e} >= clo_{c} && g0 + {e} < chi_{c}) {regs[e]} = {ldf}(q + (long long)(g0 + {e}) * si_{c});"
                 )
             L.append(f"{ind}    }}")
             L.append(f"{ind}  }}")
             L.append(f"{ind}}}")
         # 2. stages
         for si, he in enumerate(self.hes):
-            L.extend(self._emit_stage(si, he, phase))
+            L.extend(self._emit_stage(si, he, phase, fast))
         return L
 
-    def _slot_of(self, v: Value, consumer_lag: int, dj: int, phase: int) -> int:
-        m = consumer_lag - dj - v.lag  # rows behind the newest row of v
-        assert 0 <= m < v.window, (v.cname, m, v.window)
-        return (phase - m) % v.window
-
-    def _emit_stage(self, si: int, he: dict, phase: int) -> List[str]:
+    def _emit_stage(self, si: int, he: dict, phase: int, fast: bool) -> List[str]:
         V = self.V
         ind = "      "
         L: List[str] = [f"{ind}{{  // stage {si}, row r = tt - {self.lag[si]}"]
@@ -432,13 +520,13 @@ class StreamKernel:
                 if 0 <= e < V:
                     return kern.reg(v, slot, e)
                 if e < 0:
-                    src, delta, fn, tag = e + V, 1, "__shfl_up_sync", "L"
+                    src, fn, tag = e + V, "__shfl_up_sync", "L"
                 else:
-                    src, delta, fn, tag = e - V, 1, "__shfl_down_sync", "R"
+                    src, fn, tag = e - V, "__shfl_down_sync", "R"
                 nm = f"{kern.reg(v, slot, src)}_{tag}"
                 if nm not in shuf_defined:
                     shuf_defined.add(nm)
-                    self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, {delta});")
+                    self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, 1);")
                 return nm
 
             def expr(self, n):
@@ -476,7 +564,7 @@ class StreamKernel:
                     else:
                         new, prev = kern.assign_ver[id(s)]
                         ct = CT[new.dtype]
-                        slot = phase % new.window
+                        slot = kern._new_slot(new, phase)
                         for e in range(V):
                             tgt = kern.reg(new, slot, e)
                             val = f"({ct})({rhs[e]})"
@@ -489,7 +577,7 @@ class StreamKernel:
                             else:
                                 L.append(ind2 + f"{tgt} = {val};")
                         if new.store:
-                            L.extend(kern._emit_store(new, slot, ind2))
+                            L.extend(kern._emit_store(new, slot, ind2, fast))
                 elif t == "mask":
                     conds = [egs[e].expr(s["mask"]) for e in range(V)]
                     flush_pre()
@@ -526,14 +614,22 @@ class StreamKernel:
         L.append(f"{ind}}}")
         return L
 
-    def _emit_store(self, v: Value, slot: int, ind: str) -> List[str]:
+    def _emit_store(self, v: Value, slot: int, ind: str, fast: bool) -> List[str]:
         V = self.V
         c = v.cname
         e = self.hes[v.stage]["extent"]
         regs = [self.reg(v, slot, x) for x in range(V)]
         ct = CT[v.dtype]
+        rowg = f"r >= A.g.j_lo + ({e[1][0]}) && r < A.g.j_hi + ({e[1][1]})"
+        if fast:
+            g = f"{rowg} && " if self.row_guard[c] else ""
+            L = [f"{ind}if ({g}sfull_{c}) {_vec_store(ct, V, regs, f'q_{c}')}"]
+            for x in range(V):
+                L.append(f"{ind}if ({g}pe_{c}_{x}) q_{c}[{x}] = {regs[x]};")
+            L.append(f"{ind}q_{c} += sj_{c};")
+            return L
         L = [
-            f"{ind}if (own && r >= T_lo && r < T_hi && r >= A.g.j_lo + ({e[1][0]}) && r < A.g.j_hi + ({e[1][1]}) && any_{c}) {{",
+            f"{ind}if (own && r >= T_lo && r < T_hi && {rowg} && any_{c}) {{",
             f"{ind}  {ct}* q = p_{c} + (long long)r * sj_{c};",
             f"{ind}  if (full_{c}) {{",
             f"{ind}    {_vec_store(ct, V, regs, 'q + g0')}",

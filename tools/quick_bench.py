@@ -26,27 +26,22 @@ def bench(name, variant, strategy, domain, iters=20, warm=5, extra=None):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); a = ap.parse_args()
+    H=("hdiff_f32","staged","auto",(1024,1024,80))
     runs = [
-        ("hdiff_f32","default","point",(1024,1024,80)),
-        ("hdiff_f32","staged","auto",(1024,1024,80)),
+        H, H+({"prefetch":0},), H+({"prefetch":2},), H+({"prefetch":3},),
+        H+({"warps":2},), H+({"warps":8},), H+({"tile_j":64},), H+({"tile_j":16},),
+        H+({"min_blocks":5},), H+({"min_blocks":6},), H+({"prefetch":2,"min_blocks":4},), H+({"prefetch":0,"min_blocks":6},),
+        H+({"warps":2,"tile_j":64},), H+({"warps":2, "prefetch":2},), H+({"warps":1},),
+        H+({"fmad":True},),
         ("hdiff_f32","default","auto",(1024,1024,80)),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":16}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":64}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":128}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"warps":2}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"warps":8}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"tile_j":64,"warps":8}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"min_blocks":4}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"min_blocks":6,"tile_j":64}),
-        ("hdiff_f32","staged","auto",(1024,1024,80), {"fmad":True}),
         ("hdiff_f32_default_literals","staged","auto",(1024,1024,80)),
         ("copy_f64","default","auto",(1024,1024,40)),
+        ("copy_f64","default","auto",(1024,1024,40),{"prefetch":3}),
         ("laplacian_f64","default","auto",(1024,1024,40)),
-        ("upwind5_f32","default","auto",(2048,2048,20)),
         ("upwind5_f32","staged","auto",(2048,2048,20)),
+        ("upwind5_f32","staged","auto",(2048,2048,20),{"prefetch":0}),
         ("fw_pgrad_f32","staged","auto",(1024,1024,40)),
         ("fw_div_f32","staged","auto",(1024,1024,40)),
-        ("tridiagonal_f64","default","point",(512,512,160)),
     ]
     for r in runs:
         try:
