@@ -387,6 +387,9 @@ class StreamKernel:
                     w(f"  const bool pe_{v.cname}_{e} = {gate}vec_{v.cname} && !full_{v.cname} && g0 + {e} >= clo_{v.cname} && g0 + {e} < chi_{v.cname};")
                 if v.kind != "in":
                     w(f"  const bool sfull_{v.cname} = own && full_{v.cname};")
+                else:
+                    # warp-uniform: does any lane of this warp hold a partially valid vector of this stream?
+                    w(f"  const bool wpart_{v.cname} = __any_sync(0xffffffffu, " + " || ".join(f"pe_{v.cname}_{e}" for e in range(V)) + ");")
         w("  const bool allvec = " + " && ".join(f"vec_{v.cname}" for v in self.values if v.kind == "in" or v.store) + ";")
         # march ranges (in step space, relative to the tile rows)
         first_terms = [self.need_j[s][0] + self.lag[s] for s in range(self.nstages)] + [
@@ -468,9 +471,29 @@ class StreamKernel:
                 if guard:
                     L.append(f"{ind}  const int R = tt - ({v.lag}); const bool rok = {guard};")
                 g = "rok && " if guard else ""
-                L.append(f"{ind}  if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                # interior warps: one predicated 16-byte load straight into the window registers.
+                # edge warps (some lane partially valid): loads go to fresh temporaries and are merged
+                # with selects, so no load has to wait on another one's destination registers.
+                L.append(f"{ind}  if (!wpart_{c}) {{")
+                L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                L.append(f"{ind}  }} else {{")
+                tmpv = [f"tv{e}" for e in range(V)]
+                tmps = [f"ts{e}" for e in range(V)]
+                L.append(f"{ind}    {ct} " + ", ".join(f"{t} = {regs[e]}" for e, t in enumerate(tmpv)) + ";")
+                L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, tmpv, f'q_{c}', ro)}")
                 for e in range(V):
-                    L.append(f"{ind}  if ({g}pe_{c}_{e}) {regs[e]} = {ldf}(q_{c} + {e});")
+                    L.append(f"{ind}    const {ct} {tmps[e]} = ({g}pe_{c}_{e}) ? {ldf}(q_{c} + {e}) : {regs[e]};")
+                for e in range(V):
+                    L.append(f"{ind}    {regs[e]} = full_{c} ? {tmpv[e]} : {tmps[e]};")
+                L.append(f"{ind}  }}")
+                pfd = int(self.opts.get("l2_prefetch", 0))
+                if pfd > 0:
+                    # fire-and-forget L2 prefetch of the row `pfd` march steps ahead (no registers,
+                    # no scoreboard): later LDGs of this warp hit in L2 instead of waiting for HBM
+                    L.append(
+                        f"{ind}  if ((lane & 3) == 0 && full_{c} && tt - ({v.lag}) + {pfd} < T_hi + ({v.nj[1]})) "
+                        f'asm volatile("prefetch.global.L2 [%0];" :: "l"(q_{c} + {pfd} * sj_{c}));'
+                    )
                 L.append(f"{ind}  q_{c} += sj_{c};")
                 L.append(f"{ind}}}")
                 continue

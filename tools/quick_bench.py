@@ -28,20 +28,16 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); a = ap.parse_args()
     H=("hdiff_f32","staged","auto",(1024,1024,80))
     runs = [
-        H, H+({"prefetch":0},), H+({"prefetch":2},), H+({"prefetch":3},),
-        H+({"warps":2},), H+({"warps":8},), H+({"tile_j":64},), H+({"tile_j":16},),
-        H+({"min_blocks":5},), H+({"min_blocks":6},), H+({"prefetch":2,"min_blocks":4},), H+({"prefetch":0,"min_blocks":6},),
-        H+({"warps":2,"tile_j":64},), H+({"warps":2, "prefetch":2},), H+({"warps":1},),
-        H+({"fmad":True},),
-        ("hdiff_f32","default","auto",(1024,1024,80)),
-        ("hdiff_f32_default_literals","staged","auto",(1024,1024,80)),
+        H, H+({"prefetch":0},), H+({"prefetch":2},),
+        H+({"l2_prefetch":2},), H+({"l2_prefetch":4},), H+({"l2_prefetch":8},), H+({"l2_prefetch":16},),
+        H+({"l2_prefetch":4,"prefetch":0},), H+({"l2_prefetch":8,"prefetch":0},), H+({"l2_prefetch":4,"prefetch":0,"min_blocks":6},),
+        H+({"l2_prefetch":8,"prefetch":0,"min_blocks":7},), H+({"l2_prefetch":4,"min_blocks":5},), H+({"l2_prefetch":8,"min_blocks":6},),
+        H+({"min_blocks":6},), H+({"prefetch":0,"min_blocks":6},), H+({"prefetch":0,"min_blocks":7},),
+        H+({"warps":2,"l2_prefetch":4},), H+({"tile_j":64,"l2_prefetch":8},),
         ("copy_f64","default","auto",(1024,1024,40)),
-        ("copy_f64","default","auto",(1024,1024,40),{"prefetch":3}),
-        ("laplacian_f64","default","auto",(1024,1024,40)),
-        ("upwind5_f32","staged","auto",(2048,2048,20)),
+        ("copy_f64","default","auto",(1024,1024,40),{"l2_prefetch":8}),
         ("upwind5_f32","staged","auto",(2048,2048,20),{"prefetch":0}),
-        ("fw_pgrad_f32","staged","auto",(1024,1024,40)),
-        ("fw_div_f32","staged","auto",(1024,1024,40)),
+        ("upwind5_f32","staged","auto",(2048,2048,20),{"prefetch":0,"l2_prefetch":6}),
     ]
     for r in runs:
         try:
