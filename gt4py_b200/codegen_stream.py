@@ -246,6 +246,8 @@ class StreamKernel:
         if len(set(sizes)) != 1:
             raise NotStreamable("mixed item sizes among streamed API fields")
         self.V = 4 if min(sizes) == 4 else 2
+        if self.opts.get("vector_width"):
+            self.V = min(self.V, int(self.opts["vector_width"]))
         V = self.V
         for v in self.values:
             for (c, di, dj) in v.reads:
