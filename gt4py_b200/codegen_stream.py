@@ -246,20 +246,28 @@ class StreamKernel:
         if len(set(sizes)) != 1:
             raise NotStreamable("mixed item sizes among streamed API fields")
         self.V = 4 if min(sizes) == 4 else 2
+        # register budget: a thread keeps (sum of window rows) x V values live; beyond ~40 32-bit
+        # registers of window state the narrower vector (more resident warps) wins (measured on
+        # horizontal diffusion: 78.8 % vs 66.6 % of HBM peak, profiles/README.md)
+        pf = int(self.opts.get("prefetch", 1))
+        rows = sum((v.window + (pf if v.kind == "in" else 0)) * (b2ir.ITEMSIZE[v.dtype] // 4) for v in self.values)
+        vmax = self.V
+        if self.V == 4 and rows * 4 > 40:
+            self.V = 2
         if self.opts.get("vector_width"):
-            self.V = min(self.V, int(self.opts["vector_width"]))
+            self.V = min(vmax, int(self.opts["vector_width"]))
         V = self.V
         for v in self.values:
             for (c, di, dj) in v.reads:
-                if abs(di) > V:
-                    raise NotStreamable("I offset larger than the vector width")
+                if abs(di) > 8:
+                    raise NotStreamable("I offset too large")
         ins = [v for v in self.values if v.kind == "in"]
         lreach = max([0] + [-v.ni[0] for v in ins])
         rreach = max([0] + [v.ni[1] for v in ins])
         self.hl, self.hr = math.ceil(lreach / V), math.ceil(rreach / V)
         self.SQ = 32 - self.hl - self.hr
         self._choose_windows()
-        self.TJ = int(self.opts.get("tile_j", 32))
+        self.TJ = int(self.opts.get("tile_j", 64))
         self.NW = int(self.opts.get("warps", 4))
 
     def _choose_windows(self) -> None:
@@ -488,7 +496,7 @@ class StreamKernel:
                 for e in range(V):
                     L.append(f"{ind}    {regs[e]} = full_{c} ? {tmpv[e]} : {tmps[e]};")
                 L.append(f"{ind}  }}")
-                pfd = int(self.opts.get("l2_prefetch", 0))
+                pfd = int(self.opts.get("l2_prefetch", 2))
                 if pfd > 0:
                     # fire-and-forget L2 prefetch of the row `pfd` march steps ahead (no registers,
                     # no scoreboard): later LDGs of this warp hit in L2 instead of waiting for HBM
@@ -544,14 +552,12 @@ class StreamKernel:
                 e = self.elem + di
                 if 0 <= e < V:
                     return kern.reg(v, slot, e)
-                if e < 0:
-                    src, fn, tag = e + V, "__shfl_up_sync", "L"
-                else:
-                    src, fn, tag = e - V, "__shfl_down_sync", "R"
+                dl, src = divmod(e, V)  # lane distance (floor) and element inside that lane's vector
+                fn, tag = ("__shfl_up_sync", f"L{-dl}") if dl < 0 else ("__shfl_down_sync", f"R{dl}")
                 nm = f"{kern.reg(v, slot, src)}_{tag}"
                 if nm not in shuf_defined:
                     shuf_defined.add(nm)
-                    self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, 1);")
+                    self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, {abs(dl)});")
                 return nm
 
             def expr(self, n):
