@@ -1,0 +1,25 @@
+"""gt4py_b200 — B200-native stencil-execution backend for gt4py.cartesian (`backend="b200"`).
+
+Layout of the package (only what the hot path needs):
+  ir.py / from_oir.py      stencil IR (a plain-dict restatement of OIR) and the gt4py OIR -> IR lowering
+  codegen.py               point / column CUDA generator (always applicable)
+  codegen_stream.py        streaming J-march generator for PARALLEL blocks (the fast path)
+  jit.py                   nvcc -> sm_100a cubin, on-disk cache
+  csrc/, ../include/       C-ABI launcher libgt4py_b200.so (kernel launch, scratch, NCCL halo exchange)
+  runtime.py               ctypes binding, compiled-stencil object
+  storage.py               gt4py.storage-compatible pitched device allocator (no cupy)
+  stencil.py               stand-alone StencilObject mirror (runs from serialised IR, no gt4py needed)
+  backend.py               the gt4py plug-in proper (registered when gt4py is importable)
+  distributed.py           J-slab decomposition + halo exchange
+"""
+
+__version__ = "0.1.0"
+
+try:  # register backend="b200" with gt4py when the frontend is available
+    import gt4py.cartesian  # noqa: F401
+
+    from . import backend as _backend  # noqa: F401
+
+    HAVE_GT4PY = True
+except ImportError:  # stand-alone mode: serialised IR + launcher only
+    HAVE_GT4PY = False
