@@ -434,7 +434,9 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
 // ---- streams / events --------------------------------------------------------------------------
 int b200_stream_create(void** stream) {
   cudaStream_t s;
-  CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  int lo = 0, hi = 0;  // highest priority: communication kernels must not queue behind compute CTAs
+  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
   *stream = s;
   return B200_OK;
 }

@@ -37,6 +37,8 @@ res["full_kernel_us"] = timeit(lambda: fr(**f))
 res["interior_us"] = timeit(lambda: fr(**f, subbox=(0, NI, H, NJ - H)))
 res["boundary_lo_us"] = timeit(lambda: fr(**f, subbox=(0, NI, 0, H)))
 res["boundary_both_us"] = timeit(lambda: (fr(**f, subbox=(0, NI, 0, H)), fr(**f, subbox=(0, NI, NJ - H, NJ))))
+res["interior_tiles_us"] = timeit(lambda: fr(**f, subbox=(0, NI, 64, NJ - 64)))
+res["boundary_tiles_both_us"] = timeit(lambda: (fr(**f, subbox=(0, NI, 0, 64)), fr(**f, subbox=(0, NI, NJ - 64, NJ))))
 res["exchange_then_full_us"] = timeit(lambda: (ex.exchange([(f["in_field"], H, H)], stream=main), fr(**f)))
 if rank == 0: print(json.dumps(res))
 ex.close(); dist.barrier(); dist.destroy_process_group()
