@@ -180,10 +180,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--strategy", default="auto")
-    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="overlap the halo exchange with the interior tiles (N>1)")
+    ap.add_argument("--no-overlap", action="store_true", help="(default) exchange, then compute the whole slab")
+    ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.no_overlap = not args.overlap
+
+    # never hang the box: a lost peer / unmatched exchange turns into a loud non-zero exit
+    def _abort():
+        sys.stderr.write(f"bench.py: watchdog fired after {args.watchdog:.0f} s (rank {os.environ.get('RANK', '0')}) - aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+
+    wd = threading.Timer(args.watchdog, _abort)
+    wd.daemon = True
+    wd.start()
 
     if args.impl == "reference":
         run_reference(args)
@@ -288,27 +301,31 @@ def main():
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
+    # (clock sampling on rank 0 only: one nvidia-smi query stream for the whole job)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            launches += step(i)
-        e1.record()
-        barrier()
-        total_ms = e0.elapsed_time(e1)
-        # keep the sampler alive long enough for at least a few samples under load
-        if args.steps * 0 + total_ms < 400:
-            t_end = time.perf_counter() + 0.6
-            j = 0
-            while time.perf_counter() < t_end:
-                step(j)
-                j += 1
-            torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    if clocks is not None:
+        clocks.__enter__()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        launches += step(i)
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+    # Keep the same load running long enough for the clock sampler to see it.  The number of extra
+    # steps is derived from the ALL-REDUCED time, so every rank runs exactly the same count (the halo
+    # exchange is a matched send/recv: a rank-dependent count would deadlock).
+    extra_steps = int(min(4000, max(0, (700.0 - total_ms) / max(total_ms / args.steps, 1e-3))))
+    for j in range(extra_steps):
+        step(j)
+    barrier()
+    if clocks is not None:
+        clocks.__exit__(None, None, None)
     ms_per_step = total_ms / args.steps
     cells_total = NI * NJ * NK * n_gpus
     value = cells_total / ms_per_step / 1e3  # Mcell/s
@@ -424,7 +441,7 @@ def main():
                 "kernel_ms": round(kernel_ms, 5),
                 "algorithmic_bytes_per_launch": NI * NJ * NK * BYTES_PER_CELL,
             },
-            "clocks": clocks.summary(),
+            "clocks": clocks.summary() if clocks is not None else None,
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()

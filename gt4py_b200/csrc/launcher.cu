@@ -434,9 +434,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
 // ---- streams / events --------------------------------------------------------------------------
 int b200_stream_create(void** stream) {
   cudaStream_t s;
-  int lo = 0, hi = 0;  // highest priority: communication kernels must not queue behind compute CTAs
-  CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+  CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   *stream = s;
   return B200_OK;
 }
