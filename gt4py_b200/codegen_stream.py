@@ -502,7 +502,7 @@ class StreamKernel:
                     # no scoreboard): later LDGs of this warp hit in L2 instead of waiting for HBM
                     L.append(
                         f"{ind}  if ((lane & 3) == 0 && full_{c} && tt - ({v.lag}) + {pfd} < T_hi + ({v.nj[1]})) "
-                        f'asm volatile("prefetch.global.L2 [%0];" :: "l"(q_{c} + {pfd} * sj_{c}));'
+                        f"b200::prefetch_l2(q_{c} + {pfd} * sj_{c});"
                     )
                 L.append(f"{ind}  q_{c} += sj_{c};")
                 L.append(f"{ind}}}")

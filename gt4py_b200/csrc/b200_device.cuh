@@ -2,7 +2,11 @@
 // and the arithmetic helpers that give GTScript native functions NumPy-ufunc semantics
 // (reference oracle arithmetic: src/gt4py/cartesian/gtc/ufuncs.py:15-93, gtc/common.py:910-993).
 #pragma once
+#ifdef B200_HOST_EMU
+#include "cuda_shim.h"  // tests/emu: executes the generated kernels on the CPU (test infrastructure only)
+#else
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -42,6 +46,15 @@ __device__ __forceinline__ T ldro(const T* p) {  // read-only path (field not wr
 template <>
 __device__ __forceinline__ bool ldro<bool>(const bool* p) {
   return __ldg(reinterpret_cast<const unsigned char*>(p)) != 0;
+}
+
+// fire-and-forget prefetch of the line holding `p` into L2 (SASS: CCTL.E.PF2)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef B200_HOST_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
 }
 
 __device__ __forceinline__ int clampk(long long k, int lo, int hi) {

@@ -1,0 +1,57 @@
+// CPU execution shim for the GENERATED CUDA kernels — test infrastructure only (never shipped, never
+// on the product path).  The generated .cu text is compiled unchanged by g++ with -DB200_HOST_EMU and
+// run lane by lane: one OS thread per lane of a warp, warp shuffles / votes through a barrier, so the
+// code generator can be validated against the oracle on machines without a GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __grid_constant__
+#define __launch_bounds__(...)
+
+struct emu_uint3 { unsigned x, y, z; };
+extern thread_local emu_uint3 threadIdx, blockIdx;
+extern emu_uint3 blockDim, gridDim;
+
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct longlong2 { long long x, y; };
+inline int2 make_int2(int x, int y) { return {x, y}; }
+inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return {x, y}; }
+inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
+inline double2 make_double2(double x, double y) { return {x, y}; }
+inline longlong2 make_longlong2(long long x, long long y) { return {x, y}; }
+
+template <class T> inline T __ldg(const T* p) { return *p; }
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+inline double __hiloint2double(int hi, int lo) {
+  unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+  double d; std::memcpy(&d, &u, 8); return d;
+}
+using std::isfinite; using std::isinf; using std::isnan;
+
+namespace emu {
+unsigned long long exchange(unsigned long long bits, int src_lane);  // value of `bits` held by src_lane
+bool any(bool pred);
+int lane();
+template <class T> inline T shfl(T v, int src) {
+  unsigned long long b = 0; std::memcpy(&b, &v, sizeof(T));
+  b = exchange(b, src);
+  T r; std::memcpy(&r, &b, sizeof(T)); return r;
+}
+}  // namespace emu
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l - d >= 0 ? l - d : l); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l + d < 32 ? l + d : l); }
+inline bool __any_sync(unsigned, bool p) { return emu::any(p); }
