@@ -199,6 +199,10 @@ class ExprGen:
                 return f"(({CT[_CASTFUNC[fn]]})({args[0]}))"
             if fn not in _FUNC:
                 raise CodegenError(f"b200: native function {fn}")
+            if fn == "pow" and n["dtype"].startswith("float"):
+                # the upcaster leaves pow's operands alone (gtc/passes/gtir_upcaster.py:88-143):
+                # np.power(int, float) is a floating power, never an integer one
+                args = [f"(({CT[n['dtype']]})({a}))" for a in args]
             call = f"b200::{_FUNC[fn]}({', '.join(args)})"
             if fn in ("isfinite", "isinf", "isnan"):
                 return call
