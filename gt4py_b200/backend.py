@@ -228,6 +228,7 @@ class B200Backend(BaseBackend):
     storage_info: ClassVar[gt_layout.LayoutInfo] = B200_LAYOUT
     languages: ClassVar[dict] = {"computation": "cuda", "bindings": ["python"]}
     MODULE_GENERATOR_CLASS = B200ModuleGenerator
+    compile_cubin: ClassVar[bool] = True
 
     @property
     def ir_file_name(self) -> str:
@@ -262,8 +263,9 @@ class B200Backend(BaseBackend):
             b2ir.save_file(st, src_dir / self.ir_file_name)
             t1 = time.perf_counter()
             # generate + nvcc now (build errors surface at decoration time, like the reference)
-            cs = runtime.CompiledStencil(st, self.codegen_options())
-            (src_dir / (pathlib.Path(self.ir_file_name).stem + ".cu")).write_text(cs.source)
+            if self.compile_cubin:
+                cs = runtime.CompiledStencil(st, self.codegen_options())
+                (src_dir / (pathlib.Path(self.ir_file_name).stem + ".cu")).write_text(cs.source)
             if build_info is not None:
                 build_info["build_time"] = time.perf_counter() - t1
         return self.make_module()

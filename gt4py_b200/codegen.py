@@ -82,8 +82,8 @@ class FieldTable:
         self.scalars = [p for p in stencil["params"] if p["t"] == "scalar"]
 
     def _add(self, name, dtype, dims, data_dims, kind, extent):
-        if len(data_dims) > 2:
-            raise CodegenError("b200: more than two data dimensions")
+        if len(data_dims) > 4:
+            raise CodegenError("b200: more than four data dimensions")
         self.index[name] = len(self.entries)
         self.entries.append(
             {"name": name, "dtype": dtype, "dims": list(dims), "data_dims": list(data_dims), "kind": kind, "extent": extent}
@@ -511,10 +511,10 @@ def plan_to_text(plan: Dict[str, Any]) -> str:
     L.append(f"nfields {len(plan['fields'])}")
     for f in plan["fields"]:
         e = f["extent"] or [[0, 0], [0, 0]]
-        dd = f["data_dims"] + [1] * (2 - len(f["data_dims"]))
+        dd = f["data_dims"] + [1] * (4 - len(f["data_dims"]))
         L.append(
             f"field {f['name']} { {'api': 0, 'temp': 1, 'dead': 2}[f['kind']] } {f['itemsize']} "
-            f"{int(f['dims'][0])} {int(f['dims'][1])} {int(f['dims'][2])} {len(f['data_dims'])} {dd[0]} {dd[1]} "
+            f"{int(f['dims'][0])} {int(f['dims'][1])} {int(f['dims'][2])} {len(f['data_dims'])} {dd[0]} {dd[1]} {dd[2]} {dd[3]} "
             f"{e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]}"
         )
     L.append(f"scalars_size {plan['scalars_size']}")

@@ -15,16 +15,17 @@ namespace b200 {
 // One API field or backend-owned temporary, as seen by a kernel.
 //   p      : address of the element at the *origin* (domain point (0,0,0), data index 0)
 //   s[0..2]: element strides along I, J, K (0 when the field lacks the axis -> broadcast)
-//   s[3..4]: element strides of up to two data dimensions
+//   s[3..6]: element strides of up to four data dimensions
 //   klo/khi: valid K index range relative to the origin (for clipping variable-K accesses,
 //            reference: cartesian/utils/field.py:54-58)
 //   vec    : 1 when I is unit-stride and origin / J / K strides are 16-byte aligned (vector path)
 struct FieldArg {
   char* p;
-  long long s[5];
+  long long s[7];
   int klo, khi;
   int vec, _pad;
 };
+static_assert(sizeof(FieldArg) == 80, "FieldArg layout (mirrored in launcher.cu, tests/emu/emu.py)");
 
 // Launch geometry common to all kernels of a stencil call.
 struct Geom {

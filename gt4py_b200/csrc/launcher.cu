@@ -47,7 +47,7 @@ int fail(int code, const char* fmt, ...) {
 // ---- mirror of the device-side argument block (csrc/b200_device.cuh) -----------------------------
 struct FieldArg {
   char* p;
-  long long s[5];
+  long long s[7];
   int klo, khi;
   int vec, _pad;
 };
@@ -57,7 +57,7 @@ struct Geom {
   int k_lo, k_hi;
   int _pad;
 };
-static_assert(sizeof(FieldArg) == 64, "FieldArg layout");
+static_assert(sizeof(FieldArg) == 80, "FieldArg layout");
 static_assert(sizeof(Geom) == 40, "Geom layout");
 
 struct Bound {
@@ -68,7 +68,7 @@ struct Bound {
 
 struct FieldPlan {
   std::string name;
-  int is_temp, itemsize, dims[3], ndata, data[2];
+  int is_temp, itemsize, dims[3], ndata, data[4];
   int ei0, ei1, ej0, ej1;
 };
 struct KernelPlan {
@@ -127,7 +127,7 @@ int parse_plan(const char* text, b200_stencil* st) {
     } else if (tok == "field") {
       FieldPlan f;
       in >> f.name >> f.is_temp >> f.itemsize >> f.dims[0] >> f.dims[1] >> f.dims[2] >> f.ndata >> f.data[0] >>
-          f.data[1] >> f.ei0 >> f.ei1 >> f.ej0 >> f.ej1;
+          f.data[1] >> f.data[2] >> f.data[3] >> f.ei0 >> f.ei1 >> f.ej0 >> f.ej1;
       st->fields.push_back(f);
     } else if (tok == "scalars_size") {
       in >> st->scalars_size;
@@ -188,7 +188,7 @@ int parse_plan(const char* text, b200_stencil* st) {
 // Temporaries: I stride-1, padded to 32 elements so that the origin column is 128-byte aligned.
 struct TempLayout {
   size_t offset, bytes;
-  long long s[5];
+  long long s[7];
   int origin[3], shape[3];
 };
 
@@ -206,8 +206,11 @@ TempLayout temp_layout(const FieldPlan& f, const int32_t dom[3], size_t offset) 
   t.s[1] = f.dims[1] ? pitch_i : 0;
   t.s[2] = f.dims[2] ? pitch_i * nj : 0;
   long long vol = pitch_i * nj * nk;
-  t.s[3] = f.ndata > 0 ? vol * (f.ndata > 1 ? f.data[1] : 1) : 0;
-  t.s[4] = f.ndata > 1 ? vol : 0;
+  long long acc = vol;  // data dimensions are outermost, last one fastest among them
+  for (int d = f.ndata - 1; d >= 0; --d) {
+    t.s[3 + d] = acc;
+    acc *= f.data[d];
+  }
   t.origin[0] = f.dims[0] ? lead : 0;
   t.origin[1] = f.dims[1] ? -f.ej0 : 0;
   t.origin[2] = 0;
@@ -260,6 +263,8 @@ int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, i
 extern "C" {
 
 int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+size_t b200_sizeof_field(void) { return sizeof(b200_field_t); }
 
 const char* b200_last_error(void) { return g_err.c_str(); }
 
@@ -380,7 +385,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
     }
     if (fp.is_temp) {
       const TempLayout& t = tl[n];
-      for (int d = 0; d < 5; ++d) a.s[d] = t.s[d];
+      for (int d = 0; d < 7; ++d) a.s[d] = t.s[d];
       long long off = (long long)t.origin[0] * t.s[0] + (long long)t.origin[1] * t.s[1];
       a.p = (char*)st->scratch + t.offset + off * fp.itemsize;
       a.klo = 0;
@@ -393,7 +398,7 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
         continue;
       }
       long long off = 0;
-      for (int d = 0; d < 5; ++d) a.s[d] = f.strides[d];
+      for (int d = 0; d < 7; ++d) a.s[d] = f.strides[d];
       for (int d = 0; d < 3; ++d)
         if (fp.dims[d]) off += (long long)f.origin[d] * f.strides[d];
       a.p = (char*)f.data + off * fp.itemsize;

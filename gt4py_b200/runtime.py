@@ -25,7 +25,7 @@ _PKG = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libgt4py_b200.so"
 
 EXPORTED_SYMBOLS = (
-    "b200_abi_version", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
+    "b200_abi_version", "b200_sizeof_field", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
     "b200_stencil_num_fields", "b200_stencil_scalars_size", "b200_stencil_num_kernels", "b200_stencil_kernel_name",
     "b200_stencil_run", "b200_stream_create", "b200_stream_destroy", "b200_stream_synchronize",
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
 class B200Field(ctypes.Structure):
     _fields_ = [
         ("data", ctypes.c_void_p),
-        ("strides", ctypes.c_int64 * 5),
+        ("strides", ctypes.c_int64 * 7),
         ("origin", ctypes.c_int32 * 3),
         ("shape", ctypes.c_int32 * 3),
     ]
@@ -77,6 +77,7 @@ def load_library(build_if_missing: bool = True):
         pi = ctypes.POINTER(ctypes.c_int)
         sig = {
             "b200_abi_version": (ci, []),
+            "b200_sizeof_field": (cz, []),
             "b200_last_error": (ctypes.c_char_p, []),
             "b200_device_info": (ci, [ci, pi, pi, pi, pi]),
             "b200_stencil_load": (ci, [vp, cz, ctypes.c_char_p, pvp]),
@@ -104,8 +105,8 @@ def load_library(build_if_missing: bool = True):
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.b200_abi_version() != 1:
-            raise B200Error("b200: ABI version mismatch between gt4py_b200 and libgt4py_b200.so")
+        if lib.b200_abi_version() != 1 or lib.b200_sizeof_field() != ctypes.sizeof(B200Field):
+            raise B200Error("b200: ABI mismatch between gt4py_b200 and libgt4py_b200.so (rebuild the launcher)")
         _lib = lib
         return lib
 

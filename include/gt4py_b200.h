@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define B200_ABI_VERSION 1
-#define B200_MAX_DIMS 5 /* I, J, K + up to two data dimensions */
+#define B200_MAX_DIMS 7 /* I, J, K + up to four data dimensions */
 
 typedef enum b200_status {
   B200_OK = 0,
@@ -41,7 +41,7 @@ typedef enum b200_status {
  * run_computation (backend/gtc_common.py:144-168).  The launcher borrows `data` for the call. */
 typedef struct b200_field {
   void* data;                      /* device address of array element [0, 0, 0, …]; NULL = unused argument */
-  int64_t strides[B200_MAX_DIMS];  /* ELEMENT strides of I, J, K, d0, d1 (0 for an axis the field lacks)  */
+  int64_t strides[B200_MAX_DIMS];  /* ELEMENT strides of I, J, K, d0..d3 (0 for an axis the field lacks)  */
   int32_t origin[3];               /* array index of domain point (0,0,0) along I, J, K (0 if axis lacks) */
   int32_t shape[3];                /* array extents along I, J, K (1 if the field lacks the axis)          */
 } b200_field_t;
@@ -51,6 +51,8 @@ typedef struct b200_comm b200_comm_t;       /* an NCCL communicator for halo exc
 
 /* ---- library ------------------------------------------------------------------------------ */
 int b200_abi_version(void);
+/* sizeof(b200_field_t) as compiled into the library (binding self-check) */
+size_t b200_sizeof_field(void);
 const char* b200_last_error(void);
 /* Number of CUDA devices; sets *sm_major/*sm_minor of `device` when non-NULL. */
 int b200_device_info(int device, int* n_devices, int* sm_major, int* sm_minor, int* n_sms);

@@ -61,12 +61,13 @@ class EmuStencil:
         nk = dom[2] if dims[2] else 1
         lead = _align_up(-ei0, 32) if dims[0] else 0
         pitch = _align_up(lead + dom[0] + ei1, 32) if dims[0] else 1
-        dd = f["data_dims"] + [1] * (2 - len(f["data_dims"]))
         nd = int(np.prod(f["data_dims"])) if f["data_dims"] else 1
         vol = pitch * nj * nk
-        s = [1 if dims[0] else 0, pitch if dims[1] else 0, pitch * nj if dims[2] else 0,
-             vol * (dd[1] if len(f["data_dims"]) > 1 else 1) if len(f["data_dims"]) > 0 else 0,
-             vol if len(f["data_dims"]) > 1 else 0]
+        s = [1 if dims[0] else 0, pitch if dims[1] else 0, pitch * nj if dims[2] else 0, 0, 0, 0, 0]
+        acc = vol
+        for d in range(len(f["data_dims"]) - 1, -1, -1):
+            s[3 + d] = acc
+            acc *= f["data_dims"][d]
         origin = [lead if dims[0] else 0, -ej0 if dims[1] else 0, 0]
         return s, origin, vol * nd, nk
 
@@ -80,7 +81,7 @@ class EmuStencil:
         for f in plan["fields"]:
             item = f["itemsize"]
             if f["kind"] == "dead":
-                fa.append((0, [0] * 5, 0, 0, 0))
+                fa.append((0, [0] * 7, 0, 0, 0))
                 continue
             if f["kind"] == "temp":
                 s, org, nelem, nk = self._temp_layout(f, dom)
@@ -93,11 +94,11 @@ class EmuStencil:
                 continue
             arr = fields.get(f["name"])
             if arr is None:
-                fa.append((0, [0] * 5, 0, 0, 0))
+                fa.append((0, [0] * 7, 0, 0, 0))
                 continue
             es = [st // arr.itemsize for st in arr.strides]
             org = origins[f["name"]]
-            s, o3, shape3, ax = [0] * 5, [0] * 3, [1] * 3, 0
+            s, o3, shape3, ax = [0] * 7, [0] * 3, [1] * 3, 0
             for a in range(3):
                 if f["dims"][a]:
                     s[a], o3[a], shape3[a] = es[ax], int(org[ax]), arr.shape[ax]
@@ -126,8 +127,8 @@ class EmuStencil:
 
         def blob(k_lo, k_hi):
             b = struct.pack("<10i", dom[0], dom[1], dom[2], i_lo, i_hi, j_lo, j_hi, k_lo, k_hi, 0)
-            for ptr, s, klo, khi, vec in (fa if fa else [(0, [0] * 5, 0, 0, 0)]):
-                b += struct.pack("<Q5q4i", ptr, *s, klo, khi, vec, 0)
+            for ptr, s, klo, khi, vec in (fa if fa else [(0, [0] * 7, 0, 0, 0)]):
+                b += struct.pack("<Q7q4i", ptr, *s, klo, khi, vec, 0)
             b += scal
             return b + b"\0" * ((-len(b)) % 8)
 
