@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="(default) exchange, then compute the whole slab")
     ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-autotune", action="store_true", help="use the default code-generation options")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.no_overlap = not args.overlap
@@ -243,6 +244,10 @@ def main():
         )
         if s == 0:
             host_in, host_coeff = h_in, h_co
+    tuned = None
+    if not args.no_autotune:
+        # pick the fastest code-generation variant for this stencil x domain on this device
+        tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
     frozen = stencil.freeze(origin=origins, domain=domain)
 
     exchanger = None
@@ -358,7 +363,7 @@ def main():
         # pinned host mirrors with the SAME pitched layout as the device storages, so every transfer
         # is one contiguous DMA of the padded buffer (not a strided element-wise copy over PCIe)
         d_in, d_co, d_out = sets[0]["in_field"], sets[0]["coeff"], sets[0]["out_field"]
-        stencil_sync = B200Stencil(st_ir, {"strategy": args.strategy, "device_sync": False})
+        stencil_sync = B200Stencil(st_ir, {**stencil.backend_options, "device_sync": False})
 
         def host_mirror(dev, src=None):
             hp = torch.empty(dev._base.numel(), dtype=dev._base.dtype).pin_memory()
@@ -426,6 +431,8 @@ def main():
                 + ("(no overlap)" if args.no_overlap else "overlapped with interior"),
                 "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
                 "strategy": args.strategy,
+                "codegen_options": stencil.backend_options,
+                "autotune": tuned,
                 "kernels": stencil.compiled.kernel_names(),
             },
             "gpu_launches": launches,

@@ -397,10 +397,20 @@ class StreamKernel:
                     w(f"  const bool pe_{v.cname}_{e} = {gate}vec_{v.cname} && !full_{v.cname} && g0 + {e} >= clo_{v.cname} && g0 + {e} < chi_{v.cname};")
                 if v.kind != "in":
                     w(f"  const bool sfull_{v.cname} = own && full_{v.cname};")
+                    w(f"  const bool wpart_{v.cname} = __any_sync(0xffffffffu, " + " || ".join(f"pe_{v.cname}_{e}" for e in range(V)) + ");")
                 else:
                     # warp-uniform: does any lane of this warp hold a partially valid vector of this stream?
                     w(f"  const bool wpart_{v.cname} = __any_sync(0xffffffffu, " + " || ".join(f"pe_{v.cname}_{e}" for e in range(V)) + ");")
         w("  const bool allvec = " + " && ".join(f"vec_{v.cname}" for v in self.values if v.kind == "in" or v.store) + ";")
+        # warp-uniform: no lane of this warp holds a partially valid vector of any stream -> the
+        # steady loop needs one predicate per stream and nothing else
+        w("  const bool wpure = !(" + " || ".join(f"wpart_{v.cname}" for v in self.values if v.kind == "in" or v.store) + ");")
+        pfd = int(self.opts.get("l2_prefetch", 2))
+        if pfd > 0:
+            for v in self.values:
+                if v.kind == "in":
+                    w(f"  const bool pfl_{v.cname} = (lane & 3) == 0 && full_{v.cname};   // lanes that issue L2 prefetches")
+                    w(f"  const int pfe_{v.cname} = T_hi + ({v.nj[1] + v.lag - pfd});      // last step (exclusive) that may prefetch")
         # march ranges (in step space, relative to the tile rows)
         first_terms = [self.need_j[s][0] + self.lag[s] for s in range(self.nstages)] + [
             v.nj[0] + v.lag for v in self.values if v.kind == "in"
@@ -428,13 +438,21 @@ class StreamKernel:
                 ct = CT[v.dtype]
                 const = "const " if v.kind == "in" else ""
                 w(f"  {const}{ct}* q_{v.cname} = p_{v.cname} + (long long)(t - ({v.lag})) * sj_{v.cname} + g0;")
-        w(f"  if (allvec) for (; t + {U} <= T_hi + ({b}); t += {U}) {{")
-        for u in range(U):
-            w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
-            w(f"      const int tt = t + {u};")
-            L.extend(self._emit_step((ph0 + u) % U, fast=True))
-            w("    }")
-        w("  }")
+        modes = [("pure", "allvec && wpure")]
+        if not self.opts.get("pure_loop", True):
+            modes = [("fastall", "allvec")]  # one steady loop for all warps, uniform branch per load
+        # a second steady loop for warps that do hold partially valid vectors costs ~18 registers
+        # (72 -> 90 for horizontal diffusion); by default those few edge warps use the general loop
+        if self.opts.get("edge_loop", False) and self.opts.get("pure_loop", True):
+            modes.append(("fast", "allvec && !wpure"))
+        for mode, cond in modes:
+            w(f"  if ({cond}) for (; t + {U} <= T_hi + ({b}); t += {U}) {{   // steady loop ({mode})")
+            for u in range(U):
+                w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
+                w(f"      const int tt = t + {u};")
+                L.extend(self._emit_step((ph0 + u) % U, fast=mode))
+                w("    }")
+            w("  }")
         # tail: remaining steady rows + epilogue, general steps, same phase sequence
         w(f"  for (; t < t_end; t += {U}) {{")
         for u in range(U):
@@ -456,7 +474,7 @@ class StreamKernel:
         return len(gen.kernels) - 1
 
     # one march step at rotation phase `phase`
-    def _emit_step(self, phase: int, fast: bool) -> List[str]:
+    def _emit_step(self, phase: int, fast) -> List[str]:
         V = self.V
         L: List[str] = []
         ind = "      "
@@ -481,29 +499,35 @@ class StreamKernel:
                 if guard:
                     L.append(f"{ind}  const int R = tt - ({v.lag}); const bool rok = {guard};")
                 g = "rok && " if guard else ""
-                # interior warps: one predicated 16-byte load straight into the window registers.
-                # edge warps (some lane partially valid): loads go to fresh temporaries and are merged
-                # with selects, so no load has to wait on another one's destination registers.
-                L.append(f"{ind}  if (!wpart_{c}) {{")
-                L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
-                L.append(f"{ind}  }} else {{")
-                tmpv = [f"tv{e}" for e in range(V)]
-                tmps = [f"ts{e}" for e in range(V)]
-                L.append(f"{ind}    {ct} " + ", ".join(f"{t} = {regs[e]}" for e, t in enumerate(tmpv)) + ";")
-                L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, tmpv, f'q_{c}', ro)}")
-                for e in range(V):
-                    L.append(f"{ind}    const {ct} {tmps[e]} = ({g}pe_{c}_{e}) ? {ldf}(q_{c} + {e}) : {regs[e]};")
-                for e in range(V):
-                    L.append(f"{ind}    {regs[e]} = full_{c} ? {tmpv[e]} : {tmps[e]};")
-                L.append(f"{ind}  }}")
+                def edge_lines(pad):
+                    # some lane partially valid: loads go to fresh temporaries and are merged with
+                    # selects, so no load waits on another one's destination registers
+                    tmpv = [f"tv{e}" for e in range(V)]
+                    tmps = [f"ts{e}" for e in range(V)]
+                    out = [f"{pad}{ct} " + ", ".join(f"{t} = {regs[e]}" for e, t in enumerate(tmpv)) + ";"]
+                    out.append(f"{pad}if ({g}full_{c}) {_vec_load(ct, V, tmpv, f'q_{c}', ro)}")
+                    for e in range(V):
+                        out.append(f"{pad}const {ct} {tmps[e]} = ({g}pe_{c}_{e}) ? {ldf}(q_{c} + {e}) : {regs[e]};")
+                    for e in range(V):
+                        out.append(f"{pad}{regs[e]} = full_{c} ? {tmpv[e]} : {tmps[e]};")
+                    return out
+
+                if fast == "pure":
+                    # no partially valid vector in this warp: one predicated 16-byte load
+                    L.append(f"{ind}  if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                elif fast == "fastall":
+                    L.append(f"{ind}  if (!wpart_{c}) {{")
+                    L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                    L.append(f"{ind}  }} else {{")
+                    L.extend(edge_lines(ind + "    "))
+                    L.append(f"{ind}  }}")
+                else:
+                    L.extend(edge_lines(ind + "  "))
                 pfd = int(self.opts.get("l2_prefetch", 2))
                 if pfd > 0:
                     # fire-and-forget L2 prefetch of the row `pfd` march steps ahead (no registers,
                     # no scoreboard): later LDGs of this warp hit in L2 instead of waiting for HBM
-                    L.append(
-                        f"{ind}  if ((lane & 3) == 0 && full_{c} && tt - ({v.lag}) + {pfd} < T_hi + ({v.nj[1]})) "
-                        f"b200::prefetch_l2(q_{c} + {pfd} * sj_{c});"
-                    )
+                    L.append(f"{ind}  if (pfl_{c} && tt < pfe_{c}) b200::prefetch_l2(q_{c} + {pfd} * sj_{c});")
                 L.append(f"{ind}  q_{c} += sj_{c};")
                 L.append(f"{ind}}}")
                 continue
@@ -525,7 +549,7 @@ class StreamKernel:
             L.extend(self._emit_stage(si, he, phase, fast))
         return L
 
-    def _emit_stage(self, si: int, he: dict, phase: int, fast: bool) -> List[str]:
+    def _emit_stage(self, si: int, he: dict, phase: int, fast) -> List[str]:
         V = self.V
         ind = "      "
         L: List[str] = [f"{ind}{{  // stage {si}, row r = tt - {self.lag[si]}"]
@@ -645,7 +669,7 @@ class StreamKernel:
         L.append(f"{ind}}}")
         return L
 
-    def _emit_store(self, v: Value, slot: int, ind: str, fast: bool) -> List[str]:
+    def _emit_store(self, v: Value, slot: int, ind: str, fast) -> List[str]:
         V = self.V
         c = v.cname
         e = self.hes[v.stage]["extent"]
@@ -655,7 +679,7 @@ class StreamKernel:
         if fast:
             g = f"{rowg} && " if self.row_guard[c] else ""
             L = [f"{ind}if ({g}sfull_{c}) {_vec_store(ct, V, regs, f'q_{c}')}"]
-            for x in range(V):
+            for x in range(V if fast != "pure" else 0):
                 L.append(f"{ind}if ({g}pe_{c}_{x}) q_{c}[{x}] = {regs[x]};")
             L.append(f"{ind}q_{c} += sj_{c};")
             return L

@@ -306,6 +306,63 @@ class B200Stencil:
             exec_info["b200_kernel_launches"] = n
         return n
 
+    # ---- autotuning (tile shapes are a property of stencil x domain x device) --------
+    DEFAULT_CANDIDATES = (
+        {},
+        {"edge_loop": True},
+        {"pure_loop": False},
+        {"vector_width": 4},
+        {"vector_width": 4, "edge_loop": True},
+        {"vector_width": 2},
+        {"tile_j": 32},
+        {"tile_j": 128},
+        {"l2_prefetch": 4},
+        {"l2_prefetch": 1},
+        {"prefetch": 0},
+        {"warps": 2},
+        {"warps": 8},
+    )
+
+    def autotune(self, fields, params, *, domain, origin, candidates=None, iters: int = 10, verbose: bool = False):
+        """Time the code-generation variants in `candidates` (option dicts merged over the current
+        options) on the given device arguments and keep the fastest.  Outputs are overwritten.
+        Returns [(options, ms_per_launch)] sorted by time."""
+        import torch
+
+        base = dict(self.backend_options)
+        views = {n: (runtime.as_view(fields[n]) if fields.get(n) is not None else None) for n in self._field_names}
+        results = []
+        seen = set()
+        for cand in candidates if candidates is not None else self.DEFAULT_CANDIDATES:
+            opts = {**base, **cand}
+            try:
+                cs = runtime.CompiledStencil(self.ir, opts, name=self.name)
+            except Exception:  # a variant that does not apply to this stencil
+                continue
+            if cs.source in seen:
+                continue
+            seen.add(cs.source)
+            scal = cs.pack_scalars(params)
+            descs = cs.make_field_descs(views, origin)
+            for _ in range(3):
+                cs.run_descs(descs, scal, domain)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                cs.run_descs(descs, scal, domain)
+            e1.record()
+            e1.synchronize()
+            results.append((cand, e0.elapsed_time(e1) / iters, cs, opts))
+            if verbose:
+                print(f"autotune {self.name}: {cand} -> {results[-1][1]:.4f} ms")
+        if not results:
+            raise RuntimeError("autotune: no candidate could be built")
+        results.sort(key=lambda r: r[1])
+        best = results[0]
+        self.compiled, self.backend_options = best[2], best[3]
+        self.tuned = [(r[0], round(r[1], 5)) for r in results]
+        return self.tuned
+
     def freeze(self, *, origin: Dict[str, Tuple[int, ...]], domain: Tuple[int, ...]) -> "FrozenStencil":
         return FrozenStencil(self, origin, tuple(domain))
 

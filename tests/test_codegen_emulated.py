@@ -61,7 +61,14 @@ def test_subbox_launches_compose(name, variant, strategy):
     run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=4, subboxes=boxes)
 
 
-@pytest.mark.parametrize("opts", [{"vector_width": 4}, {"vector_width": 2, "tile_j": 16, "warps": 2}, {"prefetch": 0, "l2_prefetch": 0}, {"prefetch": 2, "tile_j": 8}])
+@pytest.mark.parametrize(
+    "opts",
+    [
+        {"vector_width": 4}, {"vector_width": 2, "tile_j": 16, "warps": 2}, {"prefetch": 0, "l2_prefetch": 0},
+        {"prefetch": 2, "tile_j": 8}, {"edge_loop": True}, {"pure_loop": False}, {"vector_width": 4, "edge_loop": True},
+        {"tile_j": 128}, {"l2_prefetch": 4}, {"warps": 8},
+    ],
+)  # fmt: skip
 def test_streaming_tuning_knobs_do_not_change_results(opts):
     for name in ("hdiff_f32", "upwind5_f32"):
         run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(75, 41, 2), seed=5)
