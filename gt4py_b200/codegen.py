@@ -430,7 +430,11 @@ class Generator:
                         self.steps.append({"t": "launch", "kernel": k})
             return
         if not _needs_level_sync(loop):
-            k = self.emit_seq_kernel(loop)
+            from . import codegen_column
+
+            k = codegen_column.try_emit(self, loop, self.opt)  # register k-caches + prefetch
+            if k is None:
+                k = self.emit_seq_kernel(loop)
             self.steps.append({"t": "launch", "kernel": k})
             return
         # level-by-level fallback: sections in loop order, every group its own kernel

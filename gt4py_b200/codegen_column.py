@@ -1,0 +1,326 @@
+"""Column ("K-march") generator for FORWARD / BACKWARD computation blocks.
+
+One thread owns one (i, j) column (I-coalesced across the warp) and marches along K inside the
+thread, like the baseline `seq` kernel of `codegen.py`, but with the K data flow of the column kept
+in registers instead of going back to memory for every statement:
+
+* **k-caches in registers** — a value read at a constant offset `f[di, dj, dk]` that the column has
+  already touched one level earlier (written, or read at `dk + step`) is *carried* in a register and
+  rotated at the end of the level (`sup[0,0,-1]`, `rhs[0,0,-1]` of the Thomas forward sweep,
+  `out[0,0,1]` of the back substitution): every cell is loaded at most once per sweep.
+* **one-level-ahead prefetch** — every remaining unconditional load of the level (`inf`, `diag`,
+  the not-yet-updated `sup`/`rhs`) is issued one level early into a second register, at the top of
+  the previous level's body, so the loads of level k+1 are in flight while the (long, dependent)
+  fp64 division chain of level k executes.  Little's law then holds with the ~55 resident warps/SM
+  a 512x512 plane provides, without relying on the compiler to hoist loads over possibly-aliasing
+  stores (it cannot: every field is a `double*` out of the same argument block).
+* stores are never deferred (memory is always current), so variable-K reads, later sections and
+  later kernels need no flush logic; masks stay real branches (lazy evaluation like the baseline).
+
+This is the b200 counterpart of GridTools' k-caches with fill/flush
+(reference: gtc/gtcpp/gtcpp_codegen.py:227-247, gtc/passes/oir_optimizations/caches.py) — the
+reference's cache annotations are not used, the analysis below is exact for the generated code.
+
+Anything outside the template (while loops, writes at an offset, horizontal executions with
+different extents, …) raises `NotColumnable` and the caller falls back to the baseline kernel.
+Semantics: SURVEY.md §9 (numpy backend: `for k_ in range(k, K)` / reversed, statement by statement).
+"""
+
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Set, Tuple
+
+from . import ir as b2ir
+
+CT = b2ir.CTYPE
+
+Key = Tuple[str, int, int, int]  # (field, di, dj, dk)
+
+
+class NotColumnable(Exception):
+    pass
+
+
+def _tag(key: Key) -> str:
+    def n(v):
+        return f"m{-v}" if v < 0 else f"p{v}"
+
+    name, di, dj, dk = key
+    return f"{''.join(c if c.isalnum() else '_' for c in name)}_{n(di)}{n(dj)}{n(dk)}"
+
+
+class ColumnKernel:
+    def __init__(self, gen, loop: dict, opts: Dict[str, Any]):
+        from . import codegen as cg
+
+        self.cg = cg
+        self.gen = gen
+        self.ft = gen.ft
+        self.loop = loop
+        self.opts = opts
+        self.step = 1 if loop["order"] == "forward" else -1
+        self.hes = [he for sec in loop["sections"] for he in sec["hes"]]
+        if not self.hes:
+            raise NotColumnable("empty loop")
+        ext = self.hes[0]["extent"]
+        if any(he["extent"] != ext for he in self.hes):
+            raise NotColumnable("horizontal executions with different extents")
+        self.extent = ext
+        acc = [a for he in self.hes for a in b2ir.field_accesses(he["body"])]
+        self.written: Set[str] = {a["name"] for a in acc if a["write"]}
+        for a in acc:
+            if a["write"] and (isinstance(a["off"], dict) or tuple(a["off"]) != (0, 0, 0)):
+                raise NotColumnable("write at an offset")
+        self._check_stmts([s for he in self.hes for s in he["body"]])
+        # fields whose constant-offset accesses are kept in registers: plain IJK fields
+        self.cacheable: Set[str] = set()
+        for a in acc:
+            d = self.ft.entries[self.ft.index[a["name"]]]
+            if all(d["dims"]) and not d["data_dims"]:
+                self.cacheable.add(a["name"])
+        # fields also read straight from memory (variable / absolute K index): their stores are
+        # never deferred, so those reads always see the latest value
+        self.direct_read: Set[str] = {a["name"] for a in acc if not a["write"] and isinstance(a["off"], dict)}
+        self.prefetch = bool(opts.get("seq_prefetch", True))
+
+    def _check_stmts(self, stmts) -> None:
+        for s in stmts:
+            if s["t"] == "while":
+                raise NotColumnable("while loop")
+            if s["t"] in ("mask", "hregion"):
+                self._check_stmts(s["body"])
+
+    # ---- addressing ------------------------------------------------------------------------------
+    def _addr(self, key: Key, kexpr: str) -> str:
+        name, di, dj, dk = key
+        n = self.ft.index[name]
+        f = f"A.f[{n}]"
+        off = ""
+        if di:
+            off += f" + ({di}) * {f}.s[0]"
+        if dj:
+            off += f" + ({dj}) * {f}.s[1]"
+        kk = f"({kexpr} + ({dk}))" if dk else kexpr
+        return f"c_{self.cg._cname(name)}[(long long){kk} * {f}.s[2]{off}]"
+
+    def _load(self, key: Key, kexpr: str) -> str:
+        name = key[0]
+        if name in self.written:
+            return self._addr(key, kexpr)
+        ct = CT[self.ft.entries[self.ft.index[name]]["dtype"]]
+        return f"b200::ldro<{ct}>(&{self._addr(key, kexpr)})"
+
+    def _ctype(self, key: Key) -> str:
+        return CT[self.ft.entries[self.ft.index[key[0]]]["dtype"]]
+
+    # ---- one level of one section: symbolic emission ---------------------------------------------
+    def _emit_level(self, sec: dict, live_in: Set[Key]):
+        """Emit the statements of one K level.  `live_in`: keys whose register holds the value of
+        this level on entry.  Returns (lines, exposed, final): `exposed` = keys loaded at top level
+        (unconditionally) because they were not valid; `final` = keys valid at the end of the level."""
+        kern = self
+        valid: Set[Key] = set(live_in)
+        exposed: List[Key] = []
+        touched: Set[Key] = set(live_in)
+        L: List[str] = []
+        depth = [0]
+
+        class EG(self.cg.ExprGen):
+            def __init__(self):
+                super().__init__(kern.ft, kern.written, args="A")
+                self.pre: List[str] = []
+                self.ind = "      "
+
+            def field_load(self, node):
+                off = node["off"]
+                name = node["name"]
+                if isinstance(off, dict) or node.get("data_index") or name not in kern.cacheable:
+                    return super().field_load(node)
+                key = (name, int(off[0]), int(off[1]), int(off[2]))
+                var = f"r_{_tag(key)}"
+                if key not in valid:
+                    self.pre.append(f"{var} = {kern._load(key, 'k')};")
+                    valid.add(key)
+                    touched.add(key)
+                    if depth[0] == 0:
+                        exposed.append(key)
+                return var
+
+        eg = EG()
+
+        def flush(ind):
+            for line in eg.pre:
+                L.append(ind + line)
+            eg.pre = []
+
+        def stmts(body, ind):
+            for s in body:
+                t = s["t"]
+                if t == "assign":
+                    rhs = eg.expr(s["right"])
+                    left = s["left"]
+                    if left["t"] == "scalar":
+                        flush(ind)
+                        L.append(f"{ind}{eg.locals[left['name']]} = ({CT[left['dtype']]})({rhs});")
+                        continue
+                    name = left["name"]
+                    ct = CT[kern.ft.entries[kern.ft.index[name]]["dtype"]]
+                    if name in kern.cacheable and not left.get("data_index"):
+                        key = (name, 0, 0, 0)
+                        var = f"r_{_tag(key)}"
+                        flush(ind)
+                        L.append(f"{ind}{var} = ({ct})({rhs});")
+                        # an unconditional write makes every store of this level to the cell but the
+                        # last one dead: keep the value in the register, store once at the end
+                        if depth[0] == 0 and name not in kern.direct_read:
+                            pending[key] = True
+                        if key not in pending:
+                            L.append(f"{ind}{kern._addr(key, 'k')} = {var};")
+                        # inside a branch a first definition is valid until the branch ends (dropped
+                        # there); a key that was valid before stays valid on both paths
+                        valid.add(key)
+                        touched.add(key)
+                    else:
+                        ref = eg.field_ref(left, for_write=True)  # index expressions may load
+                        flush(ind)
+                        L.append(f"{ind}{ref} = ({ct})({rhs});")
+                elif t in ("mask", "hregion"):
+                    if t == "mask":
+                        cond = eg.expr(s["mask"])
+                    else:
+                        conds = []
+                        for var, n_sym, (lo, hi) in (("i", "A.g.nI", s["i"]), ("j", "A.g.nJ", s["j"])):
+                            if lo is not None:
+                                conds.append(f"{var} >= {kern.cg._bound(lo, n_sym)}")
+                            if hi is not None:
+                                conds.append(f"{var} < {kern.cg._bound(hi, n_sym)}")
+                        cond = " && ".join(conds) if conds else "true"
+                    flush(ind)
+                    L.append(f"{ind}if ({cond}) {{")
+                    scope_base.append(set(valid))
+                    depth[0] += 1
+                    stmts(s["body"], ind + "  ")
+                    depth[0] -= 1
+                    base = scope_base.pop()
+                    # registers first defined inside the branch are undefined on the other path
+                    for key in list(valid):
+                        if key not in base:
+                            valid.discard(key)
+                    L.append(f"{ind}}}")
+                else:  # pragma: no cover
+                    raise NotColumnable(t)
+
+        scope_base: List[Set[Key]] = []
+        pending: Dict[Key, bool] = {}  # written cells whose store is deferred to the end of the level
+        for he in sec["hes"]:
+            L.append("      {")
+            saved = dict(eg.locals)
+            for d in he["locals"]:
+                eg.locals[d["name"]] = f"l_{d['name']}"
+                L.append(f"        {CT[d['dtype']]} l_{d['name']} = ({CT[d['dtype']]})0;")
+            stmts(he["body"], "        ")
+            L.append("      }")
+            eg.locals = saved
+        for key in pending:
+            L.append(f"      {kern._addr(key, 'k')} = r_{_tag(key)};")
+        return L, exposed, valid, touched
+
+    # ---- per-section plan ------------------------------------------------------------------------
+    def _plan_section(self, sec: dict):
+        step = self.step
+        _, exposed, final0, _ = self._emit_level(sec, set())
+        carried: List[Key] = []
+        passthrough: List[Key] = []
+        for key in exposed:
+            name, di, dj, dk = key
+            # nearest source along the march direction that is valid at the end of a level
+            for n in range(1, 4):
+                src = (name, di, dj, dk + n * step)
+                if src in final0:
+                    chain = [(name, di, dj, dk + m * step) for m in range(n)]
+                    for c in chain:
+                        if c not in carried:
+                            carried.append(c)
+                            if c != key and c not in exposed:
+                                passthrough.append(c)
+                    break
+        prefetched: List[Key] = []
+        if self.prefetch:
+            for key in exposed:
+                if key in carried:
+                    continue
+                name, di, dj, dk = key
+                # the location of the next level's value must not be written during this level
+                if name in self.written and dk == -step:
+                    continue
+                prefetched.append(key)
+        return carried, prefetched
+
+    # ---- kernel ----------------------------------------------------------------------------------
+    def emit(self) -> int:
+        cg, gen = self.cg, self.gen
+        name = gen._kname("col")
+        bx, by = gen.BLOCK_SEQ
+        (ei0, ei1), (ej0, ej1) = self.extent
+        L = [f'extern "C" __global__ void __launch_bounds__({bx * by}) {name}(const __grid_constant__ Args A) {{']
+        w = L.append
+        w(f"  const int i = A.g.i_lo + ({ei0}) + (int)(blockIdx.x * {bx} + threadIdx.x);")
+        w(f"  const int j = A.g.j_lo + ({ej0}) + (int)(blockIdx.y * {by} + threadIdx.y);")
+        w(f"  if (i >= A.g.i_hi + ({ei1}) || j >= A.g.j_hi + ({ej1})) return;")
+        for fname in sorted(self.cacheable):
+            n = self.ft.index[fname]
+            ct = CT[self.ft.entries[n]["dtype"]]
+            const = "" if fname in self.written else "const "
+            w(f"  {const}{ct}* const c_{cg._cname(fname)} = ({const}{ct}*)A.f[{n}].p + (long long)i * A.f[{n}].s[0] + (long long)j * A.f[{n}].s[1];")
+        fwd = self.step == 1
+        for si, sec in enumerate(self.loop["sections"]):
+            carried, prefetched = self._plan_section(sec)
+            live = set(carried) | set(prefetched)
+            body, exposed, final, touched = self._emit_level(sec, live)
+            k0 = cg._bound(sec["interval"][0], "A.g.nK")
+            k1 = cg._bound(sec["interval"][1], "A.g.nK")
+            w(f"  {{  // section {si}: carried {[_tag(c) for c in carried]}, prefetched {[_tag(p) for p in prefetched]}")
+            w(f"    const int k0 = {k0}, k1 = {k1};")
+            w("    if (k0 < k1) {")
+            for key in sorted(touched | live):
+                w(f"      {self._ctype(key)} r_{_tag(key)};")
+            first = "k0" if fwd else "(k1 - 1)"
+            for key in sorted(live):
+                w(f"      r_{_tag(key)} = {self._load(key, first)};")
+            w("      for (int k = k0; k < k1; ++k) {" if fwd else "      for (int k = k1 - 1; k >= k0; --k) {")
+            if prefetched:
+                w("      const int kn = (k + 1 < k1) ? k + 1 : k;" if fwd else "      const int kn = (k - 1 >= k0) ? k - 1 : k;")
+                for key in prefetched:
+                    w(f"      const {self._ctype(key)} n_{_tag(key)} = {self._load(key, 'kn')};")
+            L.extend(body)
+            # rotate the carried registers towards the next level (sources still hold this level)
+            order = sorted(carried, key=lambda c: c[3] * self.step)
+            for key in order:
+                src = (key[0], key[1], key[2], key[3] + self.step)
+                if src not in final and src not in carried:
+                    raise NotColumnable("carry chain")  # pragma: no cover
+                w(f"      r_{_tag(key)} = r_{_tag(src)};")
+            for key in prefetched:
+                w(f"      r_{_tag(key)} = n_{_tag(key)};")
+            w("      }")
+            w("    }")
+            w("  }")
+        w("}")
+        gen.src.append("\n".join(L))
+        gen.live |= {a["name"] for he in self.hes for a in b2ir.field_accesses(he["body"])}
+        gen.kernels.append(
+            {"name": name, "kind": "seq", "block": [bx, by, 1], "extent": [list(self.extent[0]), list(self.extent[1])],
+             "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": 0}
+        )  # fmt: skip
+        return len(gen.kernels) - 1
+
+
+def try_emit(gen, loop: dict, opts: Dict[str, Any]) -> Optional[int]:
+    """Emit `loop` (FORWARD/BACKWARD, no level synchronisation needed) as one column kernel with
+    register k-caches; returns the kernel index or None when the template does not apply."""
+    if not opts.get("seq_cache", True):
+        return None
+    try:
+        return ColumnKernel(gen, loop, opts).emit()
+    except NotColumnable:
+        return None

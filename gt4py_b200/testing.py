@@ -34,6 +34,8 @@ CASE_SPECS: Dict[str, Dict[str, Any]] = {
     "scale_param_f32": {"params": {"alpha": np.float32(1.75), "n": np.int32(3)}},
     "if_scalar_f64": {"params": {"flag": np.int32(1)}},
     "varoff_f64": {"inputs": "varoff"},
+    "col_backward_f64": {"inputs": "varoff_up"},
+    "col_multiwrite_f32": {"params": {"w": np.float32(0.625)}},
     "ints_bools": {"inputs": "ints"},
     "casts": {"inputs": "ints"},
 }
@@ -106,6 +108,8 @@ def make_case_data(stencil, name: Optional[str] = None, domain=None, seed: int =
         fields["diag"] += 1.0
     elif recipe == "varoff":
         fields["idx"] = rng.integers(-2, 3, size=shapes["idx"]).astype(np.int32)
+    elif recipe == "varoff_up":
+        fields["idx"] = rng.integers(0, 3, size=shapes["idx"]).astype(np.int32)
     elif recipe == "fastwaves":
         if "hhl" in fields and fields["hhl"] is not None:
             nk = fields["hhl"].shape[2]

@@ -72,3 +72,32 @@ def test_subbox_launches_compose(name, variant, strategy):
 def test_streaming_tuning_knobs_do_not_change_results(opts):
     for name in ("hdiff_f32", "upwind5_f32"):
         run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(75, 41, 2), seed=5)
+
+
+SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lowdim_write_f64", "col_mask_f64",
+             "col_chain_f64", "col_backward_f64", "col_multiwrite_f32"]  # fmt: skip
+
+
+@pytest.mark.parametrize("name", SEQ_CASES)
+@pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_cache": False}])
+def test_column_generator_variants(name, opts):
+    """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
+    baseline column kernel: same results on ragged domains, both lowerings"""
+    for variant, domain, seed in (("default", (37, 5, 9), 6), ("staged", (3, 2, 4), 7)):
+        es = run_emulated(name, variant, opts, domain=domain, seed=seed)
+        kinds = {k["name"].rsplit("_", 1)[-1][:3] for k in es.plan["kernels"]}
+        assert ("col" in kinds) == (opts.get("seq_cache", True)), kinds
+
+
+def test_column_generator_keeps_the_k_dataflow_in_registers():
+    """Thomas forward sweep: per level 4 prefetched loads (inf, diag, sup, rhs), 2 stores, and the
+    k-1 values of sup / rhs carried in registers (no load)."""
+    from gt4py_b200 import codegen
+
+    src, plan = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {})
+    sweep = src[src.index("section 1"):src.index("b200_tridiagonal_f64_col1")]
+    loop = sweep[sweep.index("for (int k"):]
+    assert "carried ['sup_p0p0m1', 'rhs_p0p0m1']" in sweep
+    assert loop.count("b200::ldro<double>") == 2 and loop.count("= c_sup[") == 1 and loop.count("= c_rhs[") == 1
+    assert loop.count("c_sup[(long long)k *") == 1 and loop.count("c_rhs[(long long)k *") == 1  # one store each
+    assert "(k + (-1))" not in loop

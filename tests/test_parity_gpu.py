@@ -32,10 +32,14 @@ def test_ragged_domains(name, domain):
         run_case(name, variant, None, domain=domain, seed=2)
 
 
-@pytest.mark.parametrize("name", ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64"])
+@pytest.mark.parametrize("name", ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "col_mask_f64",
+                                  "col_chain_f64", "col_backward_f64", "col_multiwrite_f32"])  # fmt: skip
 @pytest.mark.parametrize("domain", [(1, 1, 4), (70, 3, 9), (130, 37, 33)])
 def test_column_solvers_domains(name, domain):
+    """register k-cache column kernels (default), without prefetch, and the baseline column kernel"""
     run_case(name, "default", None, domain=domain, seed=4)
+    run_case(name, "staged", {"seq_prefetch": False}, domain=domain, seed=5)
+    run_case(name, "default", {"seq_cache": False}, domain=domain, seed=6)
 
 
 def test_c_order_torch_tensors_any_stride():

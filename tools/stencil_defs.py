@@ -533,3 +533,67 @@ def two_stage_par_f32(a: F32, b: F32, c: F32):
         s = a[0, 1, 0] - a[0, -1, 0]
         b = t[0, 1, 0] + t[0, -1, 0] + s[1, 0, 0] * s[-1, 0, 0]
         c = b + t
+
+
+# ---------------------------------------------------------------------------------------------
+# Column (FORWARD/BACKWARD) data-flow cases for the register k-cache generator (codegen_column.py)
+# ---------------------------------------------------------------------------------------------
+@case("col_mask_f64")
+def col_mask_f64(a: F64, b: F64, c: F64):
+    # masked writes / reads inside branches of fields that are carried along K
+    with computation(FORWARD):
+        with interval(0, 1):
+            b = a
+            c = 0.25
+        with interval(1, None):
+            if a > 0.5:
+                b = b[0, 0, -1] + a
+                c = a[0, 0, -1]
+            else:
+                b = a - c[0, 0, -1]
+            c = c[0, 0, -1] * 0.5 + b
+            if b > 1.0:
+                c = c - b[0, 0, -1]
+
+
+@case("col_chain_f64")
+def col_chain_f64(a: F64, b: F64):
+    # offsets -2 / +1 / +2 (pass-through registers), an IJ-offset read of a read-only field
+    with computation(FORWARD):
+        with interval(0, 2):
+            b = a
+        with interval(2, -2):
+            b = b[0, 0, -2] + a[0, 0, -2] + a[0, 0, 2] * a[0, 0, 1] + a[1, 0, -1]
+        with interval(-2, None):
+            b = b[0, 0, -1] - b[0, 0, -2]
+
+
+@case("col_backward_f64")
+def col_backward_f64(a: F64, idx: I32, b: F64, c: F64):
+    # BACKWARD sweep: carried b[0,0,1], a horizontal region, a variable-K read of the swept field
+    with computation(BACKWARD):
+        with interval(-1, None):
+            b = a
+            c = a
+        with interval(0, -1):
+            b = a + b[0, 0, 1] * 0.5
+            with horizontal(region[I[0], :], region[:, J[-1]]):
+                b = b * 2.0
+            c = b[0, 0, idx] + b
+            b = b + 1.0
+
+
+@case("col_multiwrite_f32", build={"literal_float_precision": 32})
+def col_multiwrite_f32(a: F32, b: F32, *, w: np.float32):
+    # several writes of the same cell per level (dead stores), a temporary carried along K
+    with computation(FORWARD):
+        with interval(0, 1):
+            t = a * w
+            b = t
+        with interval(1, None):
+            t = t[0, 0, -1] * w + a
+            b = t
+            b = b * b - a
+            if t > 1.0:
+                b = b + t[0, 0, -1]
+            t = t - 0.125
