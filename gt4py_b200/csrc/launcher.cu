@@ -108,6 +108,12 @@ struct b200_stencil {
   int device = -1;
 };
 
+struct b200_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int n_nodes = 0;
+};
+
 namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -352,6 +358,12 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       need += tl[n].bytes;
     }
   if (need > st->scratch_bytes) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(B200_ERR_INVALID,
+                  "stencil %s needs %zu bytes of scratch but the stream is being captured: call it once "
+                  "with this domain before capturing", st->name.c_str(), need);
     if (st->scratch) {
       CU(cudaStreamSynchronize(stream));
       CU(cudaFree(st->scratch));
@@ -472,6 +484,53 @@ int b200_stream_wait_event(void* stream, void* event) {
 int b200_event_elapsed_ms(void* start, void* stop, float* ms) {
   CU(cudaEventSynchronize((cudaEvent_t)stop));
   CU(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+  return B200_OK;
+}
+
+// ---- stencil sequences as CUDA graphs -------------------------------------------------
+// A time step is many small stencil calls (reference caller: examples/cartesian/demo_burgers.ipynb cell 12,
+// 3 RK stages + copies + boundary conditions); capturing the launches the calls enqueue removes the
+// per-call host overhead on replay.  Everything enqueued on `stream` (and on streams forked from it with
+// b200_event_record / b200_stream_wait_event, e.g. the halo exchange) between begin and end is captured;
+// kernel arguments (field addresses, scalars, domain) are frozen at capture time.
+int b200_graph_begin(void* stream) {
+  CU(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+  return B200_OK;
+}
+
+int b200_graph_end(void* stream, b200_graph_t** out) {
+  if (!out) return fail(B200_ERR_INVALID, "b200_graph_end: null argument");
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+  if (!graph) return fail(B200_ERR_CUDA, "stream capture was invalidated");
+  b200_graph* g = new b200_graph();
+  g->graph = graph;
+  size_t n = 0;
+  cudaError_t e = cudaGraphGetNodes(graph, nullptr, &n);
+  if (e == cudaSuccess) g->n_nodes = (int)n;
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    delete g;
+    return fail(B200_ERR_CUDA, "instantiating the captured graph failed: %s", cudaGetErrorString(e));
+  }
+  *out = g;
+  return B200_OK;
+}
+
+int b200_graph_num_nodes(const b200_graph_t* g) { return g ? g->n_nodes : B200_ERR_INVALID; }
+
+int b200_graph_launch(b200_graph_t* g, void* stream) {
+  if (!g || !g->exec) return fail(B200_ERR_INVALID, "b200_graph_launch: null graph");
+  CU(cudaGraphLaunch(g->exec, (cudaStream_t)stream));
+  return B200_OK;
+}
+
+int b200_graph_destroy(b200_graph_t* g) {
+  if (!g) return B200_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
   return B200_OK;
 }
 

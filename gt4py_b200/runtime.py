@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = (
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
     "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
     "b200_halo_exchange", "b200_pack_2d",
+    "b200_graph_begin", "b200_graph_end", "b200_graph_num_nodes", "b200_graph_launch", "b200_graph_destroy",
 )  # fmt: skip
 
 
@@ -100,6 +101,11 @@ def load_library(build_if_missing: bool = True):
             "b200_comm_destroy": (ci, [vp]),
             "b200_halo_exchange": (ci, [vp, ctypes.POINTER(B200Halo), ci, ci, ci, vp]),
             "b200_pack_2d": (ci, [vp, cz, vp, cz, cz, cz, vp]),
+            "b200_graph_begin": (ci, [vp]),
+            "b200_graph_end": (ci, [vp, pvp]),
+            "b200_graph_num_nodes": (ci, [vp]),
+            "b200_graph_launch": (ci, [vp, vp]),
+            "b200_graph_destroy": (ci, [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -192,10 +198,22 @@ def as_view(obj) -> ArrayView:
     raise TypeError(f"b200: cannot use {type(obj)} as a device field (need a CUDA array)")
 
 
+_stream_override = threading.local()
+
+
 def current_stream_handle() -> int:
+    """Stream the launcher enqueues on when a call passes none: torch's current stream, unless a
+    StencilGraph capture redirected this thread's launches to its capture stream."""
+    s = getattr(_stream_override, "handle", None)
+    if s is not None:
+        return s
     import torch
 
     return int(torch.cuda.current_stream().cuda_stream)
+
+
+def set_stream_override(handle: Optional[int]) -> None:
+    _stream_override.handle = handle
 
 
 # ---- compiled stencil -----------------------------------------------------------------------------

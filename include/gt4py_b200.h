@@ -91,6 +91,21 @@ int b200_event_record(void* event, void* stream);
 int b200_stream_wait_event(void* stream, void* event);
 int b200_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
 
+/* ---- stencil sequences as CUDA graphs (the caller side of the hot path: a model time step is a
+ *      fixed sequence of stencil calls, reference examples/cartesian/demo_burgers.ipynb cell 12; the
+ *      reference pays its Python call path, stencil_object.py:296-643, on every one of them) -------
+ * Everything enqueued on `stream` between begin and end — b200_stencil_run launches, halo exchanges,
+ * work on streams forked/joined with b200_event_record + b200_stream_wait_event — is captured instead
+ * of executed; kernel arguments are frozen at capture time.  A stencil whose scratch is not yet
+ * allocated for the domain must be called once before capture (b200_stencil_run fails loudly
+ * otherwise).  b200_graph_launch replays the whole sequence with one driver call. */
+typedef struct b200_graph b200_graph_t;
+int b200_graph_begin(void* stream);
+int b200_graph_end(void* stream, b200_graph_t** out);
+int b200_graph_num_nodes(const b200_graph_t* graph);
+int b200_graph_launch(b200_graph_t* graph, void* stream);
+int b200_graph_destroy(b200_graph_t* graph);
+
 /* ---- multi-GPU halo exchange over NCCL (an addition: the reference has no distributed path) --- */
 #define B200_NCCL_UNIQUE_ID_BYTES 128
 int b200_comm_unique_id(void* id_out /* B200_NCCL_UNIQUE_ID_BYTES */);
