@@ -163,7 +163,16 @@ def get_compiled(ir_path: str, options_json: str) -> runtime.CompiledStencil:
     key = ir_path + "|" + options_json
     cs = _COMPILED.get(key)
     if cs is None:
-        cs = runtime.CompiledStencil(b2ir.load_file(ir_path), json.loads(options_json))
+        st, opts = b2ir.load_file(ir_path), json.loads(options_json)
+        path = pathlib.Path(ir_path)
+        # warm start: the cubin + launch plan persisted next to the module in .gt_cache (generate())
+        cs = runtime.CompiledStencil.load(st, opts, path.parent, path.stem)
+        if cs is None:
+            cs = runtime.CompiledStencil(st, opts)
+            try:
+                cs.save(path.parent, path.stem)
+            except OSError:
+                pass  # read-only cache directory: keep the in-memory build
         _COMPILED[key] = cs
     return cs
 
@@ -223,6 +232,11 @@ class B200Backend(BaseBackend):
         "debug_mode": {"versioning": True, "type": bool},
         "tile_j": {"versioning": True, "type": int},
         "warps": {"versioning": True, "type": int},
+        "vector_width": {"versioning": True, "type": int},
+        "prefetch": {"versioning": True, "type": int},
+        "l2_prefetch": {"versioning": True, "type": int},
+        "seq_cache": {"versioning": True, "type": bool},
+        "seq_prefetch": {"versioning": True, "type": bool},
         "verbose": {"versioning": False, "type": bool},
     }
     storage_info: ClassVar[gt_layout.LayoutInfo] = B200_LAYOUT
@@ -236,7 +250,8 @@ class B200Backend(BaseBackend):
         return f"{caching.module_prefix}b200_ir{caching.module_postfix}.json"
 
     def codegen_options(self) -> Dict[str, Any]:
-        keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose")
+        keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
+                "l2_prefetch", "seq_cache", "seq_prefetch")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:
@@ -265,22 +280,26 @@ class B200Backend(BaseBackend):
             # generate + nvcc now (build errors surface at decoration time, like the reference)
             if self.compile_cubin:
                 cs = runtime.CompiledStencil(st, self.codegen_options())
-                (src_dir / (pathlib.Path(self.ir_file_name).stem + ".cu")).write_text(cs.source)
+                cs.save(src_dir, pathlib.Path(self.ir_file_name).stem)  # <stem>.cubin / .plan.json / .cu
             if build_info is not None:
                 build_info["build_time"] = time.perf_counter() - t1
         return self.make_module()
 
     @property
     def extra_cache_info(self) -> Dict[str, Any]:
+        def md5(path):
+            return hashlib.md5(path.read_bytes()).hexdigest() if path.exists() else ""
+
         path = self.builder.module_path.parent / self.ir_file_name
-        md5 = hashlib.md5(path.read_bytes()).hexdigest() if path.exists() else ""
-        return {**super().extra_cache_info, "b200_ir_md5": md5}
+        return {**super().extra_cache_info, "b200_ir_md5": md5(path), "b200_cubin_md5": md5(path.with_suffix(".cubin"))}
 
     @property
     def extra_cache_validation_keys(self):
+        """gt4py re-validates these against the stored cache info before reusing a cached module
+        (reference: caching.py:214-265): a tampered / truncated IR or cubin forces a rebuild."""
         keys = super().extra_cache_validation_keys
-        if self.extra_cache_info["b200_ir_md5"]:
-            keys.append("b200_ir_md5")
+        info = self.extra_cache_info
+        keys += [k for k in ("b200_ir_md5", "b200_cubin_md5") if info[k]]
         return keys
 
 

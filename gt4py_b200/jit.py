@@ -77,6 +77,28 @@ def compile_cubin(source: str, options: Optional[Dict] = None, *, name: str = "s
     return cubin.read_bytes()
 
 
+_GEN_FP = None
+
+
+def generator_fingerprint() -> str:
+    """Hash of everything that decides the generated device code besides the stencil IR and the
+    options: the code generators, the device header, the compiler.  Persisted artefacts (cubin +
+    launch plan in gt4py's .gt_cache, see backend.py) are only reused under the same fingerprint."""
+    global _GEN_FP
+    if _GEN_FP is None:
+        h = hashlib.sha256()
+        pkg = CSRC.parent
+        for f in ("codegen.py", "codegen_stream.py", "codegen_column.py", "ir.py", "csrc/b200_device.cuh"):
+            h.update((pkg / f).read_bytes())
+        try:
+            out = subprocess.run([nvcc_path(), "--version"], capture_output=True, text=True).stdout
+            h.update(out.encode())
+        except Exception:
+            h.update(b"no-nvcc")
+        _GEN_FP = h.hexdigest()[:20]
+    return _GEN_FP
+
+
 def cubin_path(source: str, options: Optional[Dict] = None, *, name: str = "stencil") -> pathlib.Path:
     flags = compile_flags(options)
     header = (CSRC / "b200_device.cuh").read_bytes()

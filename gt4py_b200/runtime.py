@@ -220,13 +220,19 @@ def set_stream_override(handle: Optional[int]) -> None:
 class CompiledStencil:
     """Generated CUDA code + launch plan of one stencil, loaded lazily into the launcher."""
 
-    def __init__(self, stencil_ir: Dict[str, Any], options: Optional[Dict[str, Any]] = None, *, name: Optional[str] = None):
+    def __init__(self, stencil_ir: Dict[str, Any], options: Optional[Dict[str, Any]] = None, *, name: Optional[str] = None,
+                 artifacts: Optional[Dict[str, Any]] = None):  # fmt: skip
         self.ir = stencil_ir
         self.options = dict(options or {})
         self.name = name or stencil_ir["name"]
-        self.source, self.plan = codegen.generate(stencil_ir, self.options)
-        self.plan_text = codegen.plan_to_text(self.plan)
-        self.cubin = jit.compile_cubin(self.source, self.options, name=codegen._cname(self.name), verbose=bool(self.options.get("verbose")))
+        if artifacts is not None:  # warm start: persisted plan + cubin, no code generation, no nvcc
+            self.source, self.plan, self.cubin = artifacts.get("source", ""), artifacts["plan"], artifacts["cubin"]
+            self.plan_text = codegen.plan_to_text(self.plan)
+        else:
+            self.source, self.plan = codegen.generate(stencil_ir, self.options)
+            self.plan_text = codegen.plan_to_text(self.plan)
+            self.cubin = jit.compile_cubin(self.source, self.options, name=codegen._cname(self.name), verbose=bool(self.options.get("verbose")))
+        self.from_artifacts = artifacts is not None
         self._handle = None
         self._api = [f for f in self.plan["fields"] if f["kind"] == "api"]
         self._scalars = self.plan["scalars"]
@@ -244,6 +250,53 @@ class CompiledStencil:
         if self.plan["scalars_size"] > pos:
             fmt += f"{self.plan['scalars_size'] - pos}x"
         return struct.Struct(fmt)
+
+    # ---- on-disk artefacts (warm starts skip code generation and nvcc) ------------------
+    def save(self, directory, stem: str) -> Dict[str, str]:
+        """Write `<stem>.cubin`, `<stem>.plan.json` (+ `<stem>.cu` for inspection) into `directory`
+        (the stencil's folder in gt4py's .gt_cache).  Returns {file name: md5} for the cache info."""
+        import hashlib
+        import json
+
+        d = pathlib.Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        meta = {
+            "generator": jit.generator_fingerprint(),
+            "options": {k: v for k, v in sorted(self.options.items()) if isinstance(v, (str, int, float, bool, type(None)))},
+            "ir": b2ir.fingerprint(self.ir),
+            "plan": self.plan,
+        }
+        files = {f"{stem}.cubin": self.cubin, f"{stem}.plan.json": json.dumps(meta, sort_keys=True, indent=1).encode()}
+        if self.source:
+            files[f"{stem}.cu"] = self.source.encode()
+        out = {}
+        for fname, data in files.items():
+            tmp = d / (fname + f".tmp{os.getpid()}")
+            tmp.write_bytes(data)
+            os.replace(tmp, d / fname)  # atomic: concurrent builders of the same stencil race benignly
+            out[fname] = hashlib.md5(data).hexdigest()
+        return out
+
+    @classmethod
+    def load(cls, stencil_ir, options, directory, stem: str, *, name: Optional[str] = None) -> Optional["CompiledStencil"]:
+        """Reuse persisted artefacts if they were produced by this generator version from this IR
+        with these options; None otherwise (the caller regenerates)."""
+        import json
+
+        d = pathlib.Path(directory)
+        try:
+            meta = json.loads((d / f"{stem}.plan.json").read_text())
+            cubin = (d / f"{stem}.cubin").read_bytes()
+        except (OSError, ValueError):
+            return None
+        opts = {k: v for k, v in sorted(dict(options or {}).items()) if isinstance(v, (str, int, float, bool, type(None)))}
+        if meta.get("generator") != jit.generator_fingerprint() or meta.get("options") != opts or not cubin:
+            return None
+        if meta.get("ir") != b2ir.fingerprint(stencil_ir):
+            return None
+        src = d / f"{stem}.cu"
+        art = {"plan": meta["plan"], "cubin": cubin, "source": src.read_text() if src.exists() else ""}
+        return cls(stencil_ir, options, name=name, artifacts=art)
 
     @property
     def handle(self):

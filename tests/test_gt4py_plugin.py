@@ -101,3 +101,45 @@ def test_plugin_lowering_equals_committed_fixture(gt):
     for k in ("params", "temporaries", "field_info", "parameter_info", "domain_info"):
         assert st[k] == ref[k], k
     assert strip(st["loops"]) == strip(ref["loops"])
+
+
+def test_artefacts_persist_in_gt_cache_and_warm_start_skips_codegen(gt, monkeypatch):
+    """cubin + launch plan live next to the generated module in gt4py's .gt_cache, are
+    covered by gt4py's cache-info validation, and a fresh process reuses them without generating or
+    compiling anything; stale artefacts (other options / generator) are rejected."""
+    import json
+    import pathlib
+
+    _, gtscript = gt
+    lap = _define(gtscript)
+    from gt4py_b200 import backend as b2backend, codegen, ir as b2ir, jit, runtime
+
+    mod = pathlib.Path(type(lap).run.__globals__["__file__"])
+    stem = [p for p in mod.parent.glob("*b200_ir*.json") if not p.name.endswith(".plan.json")][0]
+    cubin, plan = stem.with_suffix(".cubin"), stem.with_name(stem.stem + ".plan.json")
+    assert cubin.stat().st_size > 1000 and plan.exists() and stem.with_suffix(".cu").exists()
+    meta = json.loads(plan.read_text())
+    assert meta["generator"] == jit.generator_fingerprint() and meta["plan"]["kernels"]
+    cache_info = mod.with_suffix(".cacheinfo")
+    if cache_info.exists():
+        import pickle
+
+        info = pickle.loads(cache_info.read_bytes())
+        assert info.get("b200_cubin_md5") and info.get("b200_ir_md5")
+
+    # "new process": empty in-memory table, code generator and nvcc unavailable
+    b2backend._COMPILED.clear()
+    monkeypatch.setattr(codegen, "generate", lambda *a, **k: (_ for _ in ()).throw(AssertionError("codegen ran")))
+    monkeypatch.setattr(jit, "compile_cubin", lambda *a, **k: (_ for _ in ()).throw(AssertionError("nvcc ran")))
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("warm_mod", mod)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    cs = b2backend.get_compiled(m._B200_IR, m._B200_OPTS)
+    assert cs.from_artifacts and cs.cubin == cubin.read_bytes() and cs.kernel_names()
+    # different options / different generator -> not reused
+    st = b2ir.load_file(m._B200_IR)
+    assert runtime.CompiledStencil.load(st, {"strategy": "point"}, stem.parent, stem.stem) is None
+    monkeypatch.setattr(jit, "_GEN_FP", "somethingelse")
+    assert runtime.CompiledStencil.load(st, json.loads(m._B200_OPTS), stem.parent, stem.stem) is None

@@ -1,12 +1,15 @@
 #!/bin/bash
 # Run the REFERENCE's own cartesian test-suites against the b200 code generator on the CPU emulator
 # (test-only backend "b200emu", tests/emu/emu_backend.py).  Build container only (needs /root/reference).
-#   tools/run_reference_tests.sh            -> test_code_generation.py + test_suites.py (≈5 min)
+#   tools/run_reference_tests.sh            -> test_code_generation.py + test_suites.py + feature_tests/
+#                                              + test_math_functions.py (≈7 min; 191 tests on b200emu)
 set -e
 REPO="$(cd "$(dirname "$0")/.." && pwd)"
 WORK="${TMPDIR:-/tmp}/gt4py_b200_reftests"; mkdir -p "$WORK/cache"; cd "$WORK"
 export PYTHONPATH="$REPO/tests:$REPO/tools/shims:/root/reference/src:$REPO:/root/reference/tests"
 export GT_CACHE_ROOT="$WORK/cache"
-T=/root/reference/tests/cartesian_tests/integration_tests/multi_feature_tests
+I=/root/reference/tests/cartesian_tests/integration_tests
+T=$I/multi_feature_tests
+if [ $# -eq 0 ]; then set -- "$T/test_suites.py" "$T/test_math_functions.py" "$I/feature_tests"; fi
 python -m pytest -p emu.emu_backend_plugin -p no:cacheprovider --rootdir="$WORK" -c /dev/null -q -W ignore \
-    "$T/test_code_generation.py" "${@:-$T/test_suites.py}" -k b200emu
+    "$T/test_code_generation.py" "$@" -k b200emu
