@@ -447,6 +447,7 @@ class StreamKernel:
             modes.append(("fast", "allvec && !wpure"))
         for mode, cond in modes:
             w(f"  if ({cond}) for (; t + {U} <= T_hi + ({b}); t += {U}) {{   // steady loop ({mode})")
+            w(f"    B200_TRACE({0 if mode == 'pure' else 1});")
             for u in range(U):
                 w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
                 w(f"      const int tt = t + {u};")
@@ -457,6 +458,7 @@ class StreamKernel:
         w(f"  for (; t < t_end; t += {U}) {{")
         for u in range(U):
             w(f"    if (t + {u} < t_end) {{  // tail step, rotation phase {(ph0 + u) % U}")
+            w("      B200_TRACE(2);")
             w(f"      const int tt = t + {u};")
             L.extend(self._emit_step((ph0 + u) % U, fast=False))
             w("    }")

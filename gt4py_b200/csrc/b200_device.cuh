@@ -10,6 +10,14 @@
 #include <math.h>
 #include <stdint.h>
 
+// Path markers of the generated kernels: nothing on the device; counted by the CPU emulator so the
+// tests can assert WHICH loop of a kernel (steady / edge / general) a case actually went through.
+#ifdef B200_HOST_EMU
+#define B200_TRACE(slot) emu::trace(slot)
+#else
+#define B200_TRACE(slot) ((void)0)
+#endif
+
 namespace b200 {
 
 // One API field or backend-owned temporary, as seen by a kernel.

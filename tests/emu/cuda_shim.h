@@ -46,6 +46,7 @@ namespace emu {
 unsigned long long exchange(unsigned long long bits, int src_lane);  // value of `bits` held by src_lane
 bool any(bool pred);
 int lane();
+void trace(int slot);  // B200_TRACE: per-path counters, read back with emu_trace_read()
 template <class T> inline T shfl(T v, int src) {
   unsigned long long b = 0; std::memcpy(&b, &v, sizeof(T));
   b = exchange(b, src);

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import hashlib
+import mmap
 import pathlib
 import struct
 import subprocess
@@ -50,7 +51,14 @@ class EmuStencil:
                 raise RuntimeError("emulator build failed:\n" + proc.stderr[-3000:])
         self.lib = ctypes.CDLL(str(so))
         self.lib.emu_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint), ctypes.c_int]
+        self.lib.emu_trace_read.restype = ctypes.c_longlong
+        self.lib.emu_trace_read.argtypes = [ctypes.c_int, ctypes.c_int]
         self.launches = 0
+
+    def trace(self, reset=True):
+        """B200_TRACE counters: {0: steady-loop trips (pure), 1: steady-loop trips (edge/fastall),
+        2: general march steps} of the streaming kernels since the last reset."""
+        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(3)}
 
     # ---- mirror of launcher.cu ------------------------------------------------------------------
     def _temp_layout(self, f, dom):
@@ -71,8 +79,28 @@ class EmuStencil:
         origin = [lead if dims[0] else 0, -ej0 if dims[1] else 0, 0]
         return s, origin, vol * nd, nk
 
-    def run(self, fields, params, domain, origins, subbox=None):
-        """fields: name -> C-contiguous numpy arrays in IJK[+data] axis order (modified in place)."""
+    def run(self, fields, params, domain, origins, subbox=None, layout=None, guard=None):
+        """fields: name -> numpy arrays in IJK[+data] axis order (modified in place).
+
+        layout="b200": stage every field in the backend's storage layout first (I unit-stride, rows
+        padded to 32 elements, origin aligned — gt4py_b200.storage.compute_layout), which is what
+        selects the 16-byte vector path / the steady-state loop of the streaming kernels; results
+        are copied back.  guard="end"|"start": the staged buffers end (start) flush against an
+        inaccessible page, so any access outside the allocation the GPU launcher would be given
+        faults here instead of passing silently."""
+        if layout == "b200":
+            staged, keep = {}, []
+            for name, arr in fields.items():
+                if arr is None:
+                    staged[name] = None
+                    continue
+                staged[name] = _stage_b200(arr, origins[name], guard, keep)
+            self.run(staged, params, domain, origins, subbox=subbox)
+            for name, arr in fields.items():
+                if arr is not None:
+                    arr[...] = staged[name]
+            del staged, keep
+            return
         plan = self.plan
         dom = [int(d) for d in domain]
         nf = len(plan["fields"])
@@ -175,3 +203,33 @@ class EmuStencil:
     @staticmethod
     def _vec(ptr, s, item):
         return int(s[0] == 1 and ptr % 16 == 0 and (s[1] * item) % 16 == 0 and (s[2] * item) % 16 == 0)
+
+
+# ---- staging in the backend's storage layout, optionally between guard pages ------------------------
+_PAGE = mmap.PAGESIZE
+_libc = ctypes.CDLL(None, use_errno=True)
+_libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+
+
+def _stage_b200(arr: np.ndarray, origin, guard, keep) -> np.ndarray:
+    from gt4py_b200 import storage as b2storage
+
+    dims = b2storage.default_dimensions(arr.ndim)
+    lmap = b2storage.layout_map(dims)
+    org = tuple(int(o) for o in origin) + (0,) * (arr.ndim - len(origin))
+    estrides, total, lead = b2storage.compute_layout(arr.shape, lmap, arr.itemsize, b2storage.ALIGNMENT_ELEMENTS, org)
+    nbytes = (total + lead) * arr.itemsize
+    span = (nbytes + _PAGE - 1) // _PAGE * _PAGE
+    mm = mmap.mmap(-1, span + 2 * _PAGE)
+    base = ctypes.addressof(ctypes.c_char.from_buffer(mm))
+    for off in (0, _PAGE + span):
+        if _libc.mprotect(base + off, _PAGE, 0) != 0:  # PROT_NONE
+            raise OSError(ctypes.get_errno(), "mprotect")
+    # the allocation handed to the launcher is 256-byte aligned (torch caching allocator): keep that
+    # alignment so the vector-path decision is the device's; flush against the end guard if asked
+    start = _PAGE if guard != "end" else _PAGE + (span - nbytes) // 256 * 256
+    flat = np.frombuffer(mm, dtype=arr.dtype, count=total + lead, offset=start)
+    view = np.lib.stride_tricks.as_strided(flat[lead:], shape=arr.shape, strides=tuple(s * arr.itemsize for s in estrides))
+    view[...] = arr
+    keep.append((mm, flat))
+    return view

@@ -33,7 +33,15 @@ bool any(bool pred) {
   g_bar->arrive_and_wait();
   return r;
 }
+static long long g_trace[8];
+void trace(int slot) { __atomic_fetch_add(&g_trace[slot & 7], 1LL, __ATOMIC_RELAXED); }
 }  // namespace emu
+
+extern "C" long long emu_trace_read(int slot, int reset) {
+  long long v = __atomic_load_n(&emu::g_trace[slot & 7], __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&emu::g_trace[slot & 7], 0LL, __ATOMIC_RELAXED);
+  return v;
+}
 
 extern "C" void emu_launch(void (*kernel)(const void*), const void* args, const unsigned grid[3], const unsigned block[3],
                            int lockstep) {

@@ -14,7 +14,7 @@ from parity_util import compare
 CASES = testing.list_cases()
 
 
-def run_emulated(name, variant, options, domain=None, seed=0, check_golden=False, subboxes=None):
+def run_emulated(name, variant, options, domain=None, seed=0, check_golden=False, subboxes=None, layout=None, guard=None):
     st = testing.load_ir(name, variant)
     if domain is not None:
         domain = (domain[0], domain[1], max(domain[2], int(st["domain_info"]["min_k"])))
@@ -22,8 +22,9 @@ def run_emulated(name, variant, options, domain=None, seed=0, check_golden=False
     ref = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
     numpy_oracle.run(st, ref, params, domain, origins)
     es = EmuStencil(st, options, name=f"{name}.{variant}")
+    es.trace()
     for box in subboxes or [None]:
-        es.run(fields, params, domain, origins, subbox=box)
+        es.run(fields, params, domain, origins, subbox=box, layout=layout, guard=guard)
     for fname, fi in st["field_info"].items():
         if fi is not None and fields.get(fname) is not None:
             compare(name, fname, fields[fname], ref[fname])
@@ -41,6 +42,30 @@ def test_default_strategy_on_staged_lowering(name):
 
 
 @pytest.mark.parametrize("name", CASES)
+def test_default_strategy_in_the_storage_layout(name):
+    """same, with the fields in the backend's storage layout (I unit-stride, padded, aligned origin):
+    the layout gt4py.storage hands out, which selects the 16-byte vector path and the steady-state
+    loop of the streaming kernels; buffers end / start against guard pages (no out-of-bounds access)"""
+    run_emulated(name, "staged", {"strategy": "auto"}, check_golden=True, layout="b200", guard="end")
+    run_emulated(name, "default", {"strategy": "auto"}, seed=1, check_golden=True, layout="b200", guard="start")
+
+
+def test_steady_loops_are_what_the_storage_layout_runs():
+    """path coverage: with gt4py.storage-style fields most march steps of horizontal diffusion
+    go through the (pure) steady loop; with odd extents the edge warps take the edge loop when it is
+    generated and the general loop otherwise — bit-identical results either way"""
+    for opts, steady_slot in (({}, 0), ({"edge_loop": True}, 0), ({"pure_loop": False}, 1)):
+        es = run_emulated("hdiff_f32", "staged", opts, domain=(151, 70, 2), seed=12, layout="b200", guard="end")
+        tr = es.trace()
+        # (one of the three I segments of this small domain holds the odd last column -> an edge warp)
+        assert tr[steady_slot] > 0 and tr[steady_slot] * es.plan["kernels"][0]["period"] > tr[2], (opts, tr)
+        if opts.get("edge_loop"):
+            assert tr[1] > 0, tr
+    es = run_emulated("hdiff_f32", "staged", {}, domain=(151, 70, 2), seed=12)  # C-order arrays: general loop only
+    assert es.trace()[0] == 0
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_point_generator_on_default_lowering(name):
     run_emulated(name, "default", {"strategy": "point"}, seed=1, check_golden=True)
 
@@ -49,6 +74,8 @@ def test_point_generator_on_default_lowering(name):
 @pytest.mark.parametrize("domain", [(1, 1, 1), (3, 2, 1), (61, 5, 2), (129, 70, 2)])
 def test_ragged_domains_streaming(name, domain):
     run_emulated(name, "staged", {"strategy": "auto"}, domain=domain, seed=2)
+    run_emulated(name, "staged", {"strategy": "auto"}, domain=domain, seed=3, layout="b200", guard="end")
+    run_emulated(name, "staged", {"strategy": "auto"}, domain=domain, seed=3, layout="b200", guard="start")
 
 
 @pytest.mark.parametrize("name,variant", [("hdiff_f32", "staged"), ("fw_pgrad_f32", "staged"), ("upwind5_f32", "staged")])
@@ -59,6 +86,7 @@ def test_subbox_launches_compose(name, variant, strategy):
     run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=3, subboxes=boxes)
     boxes = [(0, 37, 0, nj), (37, 61, 0, 3), (37, 61, 3, nj), (61, ni, 0, nj)]
     run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=4, subboxes=boxes)
+    run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=4, subboxes=boxes, layout="b200", guard="end")
 
 
 @pytest.mark.parametrize(
@@ -72,6 +100,7 @@ def test_subbox_launches_compose(name, variant, strategy):
 def test_streaming_tuning_knobs_do_not_change_results(opts):
     for name in ("hdiff_f32", "upwind5_f32"):
         run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(75, 41, 2), seed=5)
+        run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(139, 70, 2), seed=5, layout="b200", guard="end")
 
 
 SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lowdim_write_f64", "col_mask_f64",
@@ -84,7 +113,7 @@ def test_column_generator_variants(name, opts):
     """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
     baseline column kernel: same results on ragged domains, both lowerings"""
     for variant, domain, seed in (("default", (37, 5, 9), 6), ("staged", (3, 2, 4), 7)):
-        es = run_emulated(name, variant, opts, domain=domain, seed=seed)
+        es = run_emulated(name, variant, opts, domain=domain, seed=seed, layout="b200" if seed == 6 else None, guard="end")
         kinds = {k["name"].rsplit("_", 1)[-1][:3] for k in es.plan["kernels"]}
         assert ("col" in kinds) == (opts.get("seq_cache", True)), kinds
 
