@@ -438,21 +438,47 @@ class StreamKernel:
                 ct = CT[v.dtype]
                 const = "const " if v.kind == "in" else ""
                 w(f"  {const}{ct}* q_{v.cname} = p_{v.cname} + (long long)(t - ({v.lag})) * sj_{v.cname} + g0;")
-        modes = [("pure", "allvec && wpure")]
+        streams = [v for v in self.values if v.kind == "in" or v.store]
+        # static pitch: the row pitch (J stride, in elements) of every streamed field is a compile-time
+        # constant -> row addresses inside a trip are immediates off ONE running pointer per stream
+        # (no per-step 64-bit address arithmetic); checked at run time, other pitches take the general loop
+        self.SJ = int(self.opts.get("static_pitch", 0) or 0)
+        pitch_ok = ""
+        if self.SJ:
+            w(f"  constexpr long long SJ = {self.SJ};")
+            w("  const bool spitch = " + " && ".join(f"sj_{v.cname} == SJ" for v in streams) + ";")
+            pitch_ok = " && spitch"
+        modes = [("pure", "allvec && wpure" + pitch_ok, f"T_hi + ({b})")]
         if not self.opts.get("pure_loop", True):
-            modes = [("fastall", "allvec")]  # one steady loop for all warps, uniform branch per load
+            modes = [("fastall", "allvec" + pitch_ok, f"T_hi + ({b})")]  # one steady loop for all warps, uniform branch per load
         # a second steady loop for warps that do hold partially valid vectors costs ~18 registers
         # (72 -> 90 for horizontal diffusion); by default those few edge warps use the general loop
         if self.opts.get("edge_loop", False) and self.opts.get("pure_loop", True):
-            modes.append(("fast", "allvec && !wpure"))
-        for mode, cond in modes:
-            w(f"  if ({cond}) for (; t + {U} <= T_hi + ({b}); t += {U}) {{   // steady loop ({mode})")
-            w(f"    B200_TRACE({0 if mode == 'pure' else 1});")
+            modes.append(("fast", "allvec && !wpure" + pitch_ok, f"T_hi + ({b})"))
+        # interior loop: warps whose 32 lanes all hold fully valid vectors of every stream (all but the
+        # last I segment of a row) need no per-lane load predicates at all, and run only the trips in
+        # which every L2 prefetch is allowed; what is left of the tile falls through to the loops below
+        if self.opts.get("interior_loop", False) and self.opts.get("pure_loop", True) and not any(self.row_guard.values()):
+            w("  const bool winterior = __all_sync(0xffffffffu, " + " && ".join(
+                f"full_{v.cname}" if v.kind == "in" else f"(!own || full_{v.cname})" for v in streams) + ");")
+            lim = [f"T_hi + ({b})"] + ([f"pfe_{v.cname}" for v in self.values if v.kind == "in"] if pfd > 0 else [])
+            w("  int t_int = " + lim[0] + ";")
+            for x in lim[1:]:
+                w(f"  t_int = t_int < {x} ? t_int : {x};")
+            if pfd > 0:
+                w("  const bool pf_lane = (lane & 3) == 0;")
+            modes.insert(0, ("interior", "allvec && wpure && winterior" + pitch_ok, "t_int"))
+        for mode, cond, bound in modes:
+            w(f"  if ({cond}) for (; t + {U} <= {bound}; t += {U}) {{   // steady loop ({mode})")
+            w(f"    B200_TRACE({3 if mode == 'interior' else (0 if mode == 'pure' else 1)});")
             for u in range(U):
                 w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
                 w(f"      const int tt = t + {u};")
-                L.extend(self._emit_step((ph0 + u) % U, fast=mode))
+                L.extend(self._emit_step((ph0 + u) % U, fast=mode, u=u))
                 w("    }")
+            if self.SJ:
+                for v in streams:
+                    w(f"    q_{v.cname} += {U} * SJ;")
             w("  }")
         # tail: remaining steady rows + epilogue, general steps, same phase sequence
         w(f"  for (; t < t_end; t += {U}) {{")
@@ -476,10 +502,11 @@ class StreamKernel:
         return len(gen.kernels) - 1
 
     # one march step at rotation phase `phase`
-    def _emit_step(self, phase: int, fast) -> List[str]:
+    def _emit_step(self, phase: int, fast, u: int = 0) -> List[str]:
         V = self.V
         L: List[str] = []
         ind = "      "
+        self._u = u
         # 0. shifting windows (values whose window does not divide the rotation period)
         for v in self.values:
             if v.shift and v.window > 1:
@@ -501,36 +528,45 @@ class StreamKernel:
                 if guard:
                     L.append(f"{ind}  const int R = tt - ({v.lag}); const bool rok = {guard};")
                 g = "rok && " if guard else ""
-                def edge_lines(pad):
+                def edge_lines(pad, qa):
                     # some lane partially valid: loads go to fresh temporaries and are merged with
                     # selects, so no load waits on another one's destination registers
                     tmpv = [f"tv{e}" for e in range(V)]
                     tmps = [f"ts{e}" for e in range(V)]
                     out = [f"{pad}{ct} " + ", ".join(f"{t} = {regs[e]}" for e, t in enumerate(tmpv)) + ";"]
-                    out.append(f"{pad}if ({g}full_{c}) {_vec_load(ct, V, tmpv, f'q_{c}', ro)}")
+                    out.append(f"{pad}if ({g}full_{c}) {_vec_load(ct, V, tmpv, qa, ro)}")
                     for e in range(V):
-                        out.append(f"{pad}const {ct} {tmps[e]} = ({g}pe_{c}_{e}) ? {ldf}(q_{c} + {e}) : {regs[e]};")
+                        out.append(f"{pad}const {ct} {tmps[e]} = ({g}pe_{c}_{e}) ? {ldf}({qa} + {e}) : {regs[e]};")
                     for e in range(V):
                         out.append(f"{pad}{regs[e]} = full_{c} ? {tmpv[e]} : {tmps[e]};")
                     return out
 
-                if fast == "pure":
+                qa = self._row_addr(c)
+                if fast == "interior":
+                    # every lane of the warp holds a fully valid vector: unconditional 16-byte load
+                    L.append(f"{ind}  {_vec_load(ct, V, regs, qa, ro)}")
+                elif fast == "pure":
                     # no partially valid vector in this warp: one predicated 16-byte load
-                    L.append(f"{ind}  if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                    L.append(f"{ind}  if ({g}full_{c}) {_vec_load(ct, V, regs, qa, ro)}")
                 elif fast == "fastall":
                     L.append(f"{ind}  if (!wpart_{c}) {{")
-                    L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, regs, f'q_{c}', ro)}")
+                    L.append(f"{ind}    if ({g}full_{c}) {_vec_load(ct, V, regs, qa, ro)}")
                     L.append(f"{ind}  }} else {{")
-                    L.extend(edge_lines(ind + "    "))
+                    L.extend(edge_lines(ind + "    ", qa))
                     L.append(f"{ind}  }}")
                 else:
-                    L.extend(edge_lines(ind + "  "))
+                    L.extend(edge_lines(ind + "  ", qa))
                 pfd = int(self.opts.get("l2_prefetch", 2))
                 if pfd > 0:
                     # fire-and-forget L2 prefetch of the row `pfd` march steps ahead (no registers,
                     # no scoreboard): later LDGs of this warp hit in L2 instead of waiting for HBM
-                    L.append(f"{ind}  if (pfl_{c} && tt < pfe_{c}) b200::prefetch_l2(q_{c} + {pfd} * sj_{c});")
-                L.append(f"{ind}  q_{c} += sj_{c};")
+                    pfa = self._row_addr(c, pfd)
+                    if fast == "interior":
+                        L.append(f"{ind}  if (pf_lane) b200::prefetch_l2({pfa});")
+                    else:
+                        L.append(f"{ind}  if (pfl_{c} && tt < pfe_{c}) b200::prefetch_l2({pfa});")
+                if not self.SJ:
+                    L.append(f"{ind}  q_{c} += sj_{c};")
                 L.append(f"{ind}}}")
                 continue
             L.append(f"{ind}{{ const int R = tt - ({v.lag});")
@@ -550,6 +586,13 @@ class StreamKernel:
         for si, he in enumerate(self.hes):
             L.extend(self._emit_stage(si, he, phase, fast))
         return L
+
+    def _row_addr(self, c: str, ahead: int = 0) -> str:
+        """Address of this lane's vector in the row the current steady step touches (+ `ahead` rows)."""
+        if self.SJ:
+            k = self._u + ahead
+            return f"(q_{c} + {k} * SJ)" if k else f"q_{c}"
+        return f"(q_{c} + {ahead} * sj_{c})" if ahead else f"q_{c}"
 
     def _emit_stage(self, si: int, he: dict, phase: int, fast) -> List[str]:
         V = self.V
@@ -680,10 +723,14 @@ class StreamKernel:
         rowg = f"r >= A.g.j_lo + ({e[1][0]}) && r < A.g.j_hi + ({e[1][1]})"
         if fast:
             g = f"{rowg} && " if self.row_guard[c] else ""
-            L = [f"{ind}if ({g}sfull_{c}) {_vec_store(ct, V, regs, f'q_{c}')}"]
+            qa = self._row_addr(c)
+            if fast == "interior":
+                return [f"{ind}if (own) {_vec_store(ct, V, regs, qa)}"] + ([] if self.SJ else [f"{ind}q_{c} += sj_{c};"])
+            L = [f"{ind}if ({g}sfull_{c}) {_vec_store(ct, V, regs, qa)}"]
             for x in range(V if fast != "pure" else 0):
-                L.append(f"{ind}if ({g}pe_{c}_{x}) q_{c}[{x}] = {regs[x]};")
-            L.append(f"{ind}q_{c} += sj_{c};")
+                L.append(f"{ind}if ({g}pe_{c}_{x}) ({qa})[{x}] = {regs[x]};")
+            if not self.SJ:
+                L.append(f"{ind}q_{c} += sj_{c};")
             return L
         L = [
             f"{ind}if (own && r >= T_lo && r < T_hi && {rowg} && any_{c}) {{",

@@ -307,13 +307,25 @@ class B200Stencil:
         return n
 
     # ---- autotuning (tile shapes are a property of stencil x domain x device) --------
+    #: code-generation variants tried by autotune(); "auto" pitch = the common row pitch of the arguments
     DEFAULT_CANDIDATES = (
         {},
+        {"static_pitch": "auto"},
+        {"interior_loop": True},
+        {"interior_loop": True, "static_pitch": "auto"},
+        {"interior_loop": True, "static_pitch": "auto", "l2_prefetch": 4},
+        {"interior_loop": True, "static_pitch": "auto", "l2_prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tile_j": 128},
+        {"interior_loop": True, "static_pitch": "auto", "tile_j": 32},
+        {"interior_loop": True, "static_pitch": "auto", "warps": 8},
+        {"interior_loop": True, "static_pitch": "auto", "warps": 2},
+        {"interior_loop": True, "static_pitch": "auto", "prefetch": 0},
+        {"interior_loop": True, "static_pitch": "auto", "vector_width": 4},
+        {"interior_loop": True, "static_pitch": "auto", "vector_width": 4, "prefetch": 0},
+        {"interior_loop": True, "static_pitch": "auto", "min_blocks": 9},
         {"edge_loop": True},
         {"pure_loop": False},
         {"vector_width": 4},
-        {"vector_width": 4, "edge_loop": True},
-        {"vector_width": 2},
         {"tile_j": 32},
         {"tile_j": 128},
         {"l2_prefetch": 4},
@@ -323,17 +335,45 @@ class B200Stencil:
         {"warps": 8},
     )
 
+    @staticmethod
+    def resolve_candidate(cand: Dict[str, Any], views: Dict[str, Any]) -> Optional[Dict[str, Any]]:
+        """Fill argument-dependent values of a candidate: static_pitch="auto" -> the J stride shared
+        by all 3-D arguments (None when they do not share one)."""
+        cand = dict(cand)
+        if cand.get("static_pitch") == "auto":
+            pitches = {v.strides[1] for v in views.values() if v is not None and v.ndim >= 3 and v.strides[0] == 1}
+            if len(pitches) != 1:
+                return None
+            cand["static_pitch"] = int(pitches.pop())
+        return cand
+
     def autotune(self, fields, params, *, domain, origin, candidates=None, iters: int = 10, verbose: bool = False):
         """Time the code-generation variants in `candidates` (option dicts merged over the current
-        options) on the given device arguments and keep the fastest.  Outputs are overwritten.
+        options) on the given device arguments and keep the fastest one whose written fields are
+        bit-identical to the first candidate's (the current options).  Outputs are overwritten.
         Returns [(options, ms_per_launch)] sorted by time."""
         import torch
 
         base = dict(self.backend_options)
         views = {n: (runtime.as_view(fields[n]) if fields.get(n) is not None else None) for n in self._field_names}
-        results = []
+        written = [n for n, fi in self.field_info.items() if fi is not None and fi.access in ("WRITE", "READ_WRITE") and views.get(n) is not None]
+        if any(self.field_info[n].access == "READ_WRITE" for n in written):
+            raise ValueError("autotune: stencils that update a field in place cannot be re-run for timing")
+
+        def tensors():
+            ts = [fields[n].torch() if isinstance(fields[n], b2storage.DeviceArray) else fields[n] for n in written]
+            return [t for t in ts if hasattr(t, "clone") and hasattr(t, "zero_")]
+
+        def snapshot():
+            return [t.clone() for t in tensors()]
+
+        results, rejected = [], []
         seen = set()
+        expect = None
         for cand in candidates if candidates is not None else self.DEFAULT_CANDIDATES:
+            cand = self.resolve_candidate(cand, views)
+            if cand is None:
+                continue
             opts = {**base, **cand}
             try:
                 cs = runtime.CompiledStencil(self.ir, opts, name=self.name)
@@ -344,8 +384,16 @@ class B200Stencil:
             seen.add(cs.source)
             scal = cs.pack_scalars(params)
             descs = cs.make_field_descs(views, origin)
+            for t in tensors():
+                t.zero_()  # a variant that writes nothing must not inherit the previous one's result
             for _ in range(3):
                 cs.run_descs(descs, scal, domain)
+            got = snapshot()
+            if expect is None:
+                expect = got  # the current options are the reference: parity-tested against the oracle
+            elif any(not torch.equal(a, b) for a, b in zip(expect, got)):
+                rejected.append(cand)
+                continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(iters):
@@ -361,6 +409,7 @@ class B200Stencil:
         best = results[0]
         self.compiled, self.backend_options = best[2], best[3]
         self.tuned = [(r[0], round(r[1], 5)) for r in results]
+        self.tune_rejected = rejected
         return self.tuned
 
     def freeze(self, *, origin: Dict[str, Tuple[int, ...]], domain: Tuple[int, ...]) -> "FrozenStencil":

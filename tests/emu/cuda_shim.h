@@ -56,3 +56,4 @@ template <class T> inline T shfl(T v, int src) {
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l - d >= 0 ? l - d : l); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l + d < 32 ? l + d : l); }
 inline bool __any_sync(unsigned, bool p) { return emu::any(p); }
+inline bool __all_sync(unsigned, bool p) { return !emu::any(!p); }

@@ -63,6 +63,13 @@ def test_steady_loops_are_what_the_storage_layout_runs():
             assert tr[1] > 0, tr
     es = run_emulated("hdiff_f32", "staged", {}, domain=(151, 70, 2), seed=12)  # C-order arrays: general loop only
     assert es.trace()[0] == 0
+    # interior loop (no per-lane predicates) + compile-time row pitch: taken by the full-width warps
+    es = run_emulated("hdiff_f32", "staged", {"interior_loop": True, "static_pitch": 160}, domain=(151, 70, 2), seed=12, layout="b200", guard="end")
+    tr = es.trace()
+    assert tr[3] > 0 and tr[0] > 0, tr
+    es = run_emulated("hdiff_f32", "staged", {"interior_loop": True, "static_pitch": 192}, domain=(151, 70, 2), seed=12, layout="b200", guard="end")
+    tr = es.trace()
+    assert tr[3] == 0 and tr[0] == 0 and tr[2] > 0, tr
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -95,6 +102,10 @@ def test_subbox_launches_compose(name, variant, strategy):
         {"vector_width": 4}, {"vector_width": 2, "tile_j": 16, "warps": 2}, {"prefetch": 0, "l2_prefetch": 0},
         {"prefetch": 2, "tile_j": 8}, {"edge_loop": True}, {"pure_loop": False}, {"vector_width": 4, "edge_loop": True},
         {"tile_j": 128}, {"l2_prefetch": 4}, {"warps": 8},
+        {"interior_loop": True}, {"static_pitch": 160}, {"interior_loop": True, "static_pitch": 160},
+        {"interior_loop": True, "static_pitch": 160, "vector_width": 4, "prefetch": 0},
+        {"interior_loop": True, "static_pitch": 160, "l2_prefetch": 0, "tile_j": 32, "warps": 2},
+        {"interior_loop": True, "static_pitch": 192},  # pitch of the arguments differs -> general loop, same result
     ],
 )  # fmt: skip
 def test_streaming_tuning_knobs_do_not_change_results(opts):

@@ -1,0 +1,36 @@
+"""-m gpu: every code-generation variant the autotuner may pick is bit-identical to the default one
+(and the default one to the oracle) on the device, in the storage layout, incl. odd extents."""
+
+import numpy as np
+import pytest
+
+from gt4py_b200 import testing
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,domain", [("hdiff_f32", (389, 200, 3)), ("upwind5_f32", (262, 150, 2)), ("hdiff_f64", (130, 131, 2))])
+def test_autotune_candidates_are_bit_identical(name, domain):
+    import torch
+
+    from gt4py_b200 import storage
+    from gt4py_b200.stencil import B200Stencil
+    from oracle import numpy_oracle
+
+    st = testing.load_ir(name, "staged")
+    fields, params, origins, domain = testing.make_case_data(st, name, domain=domain, seed=31)
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    dev = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+    stencil = B200Stencil(st, {"device_sync": False})
+    tuned = stencil.autotune(dev, params, domain=domain, origin=origins, iters=2)
+    assert stencil.tune_rejected == [], stencil.tune_rejected
+    assert len(tuned) >= 10
+    assert any("static_pitch" in c for c, _ in tuned) and any(c.get("interior_loop") for c, _ in tuned)
+    # the winner, through the public call
+    for fname in testing.written_fields(st):
+        dev[fname].fill(0)
+    stencil(**dev, **params, origin=origins, domain=domain)
+    torch.cuda.synchronize()
+    for fname in testing.written_fields(st):
+        np.testing.assert_array_equal(dev[fname].get(), ref[fname], err_msg=f"{name}:{fname} {stencil.backend_options}")
