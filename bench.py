@@ -461,6 +461,7 @@ def main():
                 "strategy": args.strategy,
                 "codegen_options": stencil.backend_options,
                 "autotune": tuned,
+                "autotune_rejected": getattr(stencil, "tune_rejected", None),
                 "kernels": stencil.compiled.kernel_names(),
             },
             "gpu_launches": launches,
