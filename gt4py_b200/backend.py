@@ -237,6 +237,9 @@ class B200Backend(BaseBackend):
         "l2_prefetch": {"versioning": True, "type": int},
         "seq_cache": {"versioning": True, "type": bool},
         "seq_prefetch": {"versioning": True, "type": bool},
+        "interior_loop": {"versioning": True, "type": bool},
+        "static_pitch": {"versioning": True, "type": int},
+        "specialize": {"versioning": True, "type": str},  # "off" | "lazy": per-pitch kernels at first call
         "verbose": {"versioning": False, "type": bool},
     }
     storage_info: ClassVar[gt_layout.LayoutInfo] = B200_LAYOUT
@@ -251,7 +254,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -233,6 +233,11 @@ class CompiledStencil:
             self.plan_text = codegen.plan_to_text(self.plan)
             self.cubin = jit.compile_cubin(self.source, self.options, name=codegen._cname(self.name), verbose=bool(self.options.get("verbose")))
         self.from_artifacts = artifacts is not None
+        # specialize="lazy": at the first call with a given row pitch, compile (once, disk-cached) the
+        # variant of the streaming kernels with that pitch as a compile-time constant + the interior
+        # steady loop (codegen_stream.py) and use it for every later call with the same pitch
+        self._specialize = str(self.options.get("specialize", "off"))
+        self._special: Dict[int, "CompiledStencil"] = {}
         self._handle = None
         self._api = [f for f in self.plan["fields"] if f["kind"] == "api"]
         self._scalars = self.plan["scalars"]
@@ -355,7 +360,33 @@ class CompiledStencil:
         descs = self.make_field_descs(views, origins)
         return self.run_descs(descs, scalars, domain, stream=stream, subbox=subbox)
 
+    def specialized_for(self, descs) -> "CompiledStencil":
+        """The compiled variant to run for these field descriptors (self unless specialize="lazy")."""
+        if self._specialize != "lazy" or "static_pitch" in self.options:
+            return self
+        if not any(k["kind"] == "stream" for k in self.plan["kernels"]):
+            return self
+        pitches = set()
+        for n, f in enumerate(self._api):
+            d = descs[n]
+            if d.data and all(f["dims"]) and d.strides[0] == 1:
+                pitches.add(int(d.strides[1]))
+        if len(pitches) != 1:
+            return self
+        pitch = pitches.pop()
+        cs = self._special.get(pitch)
+        if cs is None:
+            opts = {**self.options, "static_pitch": pitch, "interior_loop": True, "specialize": "off"}
+            cs = CompiledStencil(self.ir, opts, name=self.name)
+            self._special[pitch] = cs
+        return cs
+
     def run_descs(self, descs, scalars: bytes, domain, *, stream=None, subbox=None) -> int:
+        target = self.specialized_for(descs)
+        if target is not self:
+            n = target.run_descs(descs, scalars, domain, stream=stream, subbox=subbox)
+            self.last_launches = n
+            return n
         lib = load_library()
         dom = (ctypes.c_int32 * 3)(*[int(d) for d in domain])
         sb = (ctypes.c_int32 * 4)(*[int(x) for x in subbox]) if subbox is not None else None

@@ -50,3 +50,28 @@ def test_bad_plan_is_rejected():
     h = ctypes.c_void_p()
     rc = lib.b200_stencil_load(b"xx", 2, b"not a plan", ctypes.byref(h))
     assert rc < 0 and b"plan" in lib.b200_last_error()
+
+
+def test_lazy_pitch_specialisation_selects_one_variant_per_pitch():
+    """specialize="lazy": descriptors with a common unit-stride row pitch get the static-pitch +
+    interior-loop variant of the streaming kernels (compiled once per pitch); anything else keeps
+    the generic kernels.  Code generation + nvcc only — nothing is launched here."""
+    from gt4py_b200 import testing
+
+    st = testing.load_ir("hdiff_f32", "staged")
+    cs = runtime.CompiledStencil(st, {"specialize": "lazy"})
+    org = {n: (2, 2, 0) for n in ("in_field", "out_field", "coeff")}
+
+    def descs(pitch, si=1):
+        v = runtime.ArrayView(0x10000, (36, 20, 4), (si, pitch, pitch * 20), "float32")
+        return cs.make_field_descs({"in_field": v, "out_field": v, "coeff": v}, org)
+
+    a = cs.specialized_for(descs(64))
+    assert a is not cs and a.options["static_pitch"] == 64 and a.options["interior_loop"]
+    assert "constexpr long long SJ = 64;" in a.source and "winterior" in a.source
+    assert cs.specialized_for(descs(64)) is a  # cached
+    assert cs.specialized_for(descs(96)).options["static_pitch"] == 96
+    assert cs.specialized_for(descs(64, si=2)) is cs  # not I-contiguous: generic kernels
+    assert runtime.CompiledStencil(st, {}).specialized_for(descs(64)).options.get("static_pitch") is None
+    col = runtime.CompiledStencil(testing.load_ir("tridiagonal_f64"), {"specialize": "lazy"})
+    assert not col._special and all(k["kind"] != "stream" for k in col.plan["kernels"])
