@@ -8,9 +8,9 @@ in registers instead of going back to memory for every statement:
   already touched one level earlier (written, or read at `dk + step`) is *carried* in a register and
   rotated at the end of the level (`sup[0,0,-1]`, `rhs[0,0,-1]` of the Thomas forward sweep,
   `out[0,0,1]` of the back substitution): every cell is loaded at most once per sweep.
-* **one-level-ahead prefetch** — every remaining unconditional load of the level (`inf`, `diag`,
-  the not-yet-updated `sup`/`rhs`) is issued one level early into a second register, at the top of
-  the previous level's body, so the loads of level k+1 are in flight while the (long, dependent)
+* **look-ahead prefetch** (`seq_prefetch` = depth, default 1 level) — every remaining unconditional
+  load of the level (`inf`, `diag`, the not-yet-updated `sup`/`rhs`) is issued `depth` levels early
+  into a register pipeline, at the top of an earlier level's body, so the loads of level k+1 are in flight while the (long, dependent)
   fp64 division chain of level k executes.  Little's law then holds with the ~55 resident warps/SM
   a 512x512 plane provides, without relying on the compiler to hoist loads over possibly-aliasing
   stores (it cannot: every field is a `double*` out of the same argument block).
@@ -81,7 +81,9 @@ class ColumnKernel:
         # fields also read straight from memory (variable / absolute K index): their stores are
         # never deferred, so those reads always see the latest value
         self.direct_read: Set[str] = {a["name"] for a in acc if not a["write"] and isinstance(a["off"], dict)}
-        self.prefetch = bool(opts.get("seq_prefetch", True))
+        pf = opts.get("seq_prefetch", True)
+        self.depth = max(0, int(pf)) if not isinstance(pf, bool) else (1 if pf else 0)  # levels of load look-ahead
+        self.prefetch = self.depth > 0
 
     def _check_stmts(self, stmts) -> None:
         for s in stmts:
@@ -250,8 +252,8 @@ class ColumnKernel:
                 if key in carried:
                     continue
                 name, di, dj, dk = key
-                # the location of the next level's value must not be written during this level
-                if name in self.written and dk == -step:
+                # the cell loaded `depth` levels early must not be written by the levels in between
+                if name in self.written and -self.depth <= dk * step < 0:
                     continue
                 prefetched.append(key)
         return carried, prefetched
@@ -285,11 +287,19 @@ class ColumnKernel:
             for key in sorted(touched | live):
                 w(f"      {self._ctype(key)} r_{_tag(key)};")
             first = "k0" if fwd else "(k1 - 1)"
+            D = self.depth
+
+            def ahead(base: str, n: int) -> str:  # level n march steps after `base`, clamped to the section
+                return f"(({base}) + {n} < k1 ? ({base}) + {n} : k1 - 1)" if fwd else f"(({base}) - {n} >= k0 ? ({base}) - {n} : k0)"
+
             for key in sorted(live):
                 w(f"      r_{_tag(key)} = {self._load(key, first)};")
+            for key in prefetched:  # look-ahead pipeline: p<j> holds the value of the level j steps ahead
+                for j in range(1, D):
+                    w(f"      {self._ctype(key)} p{j}_{_tag(key)} = {self._load(key, ahead(first, j))};")
             w("      for (int k = k0; k < k1; ++k) {" if fwd else "      for (int k = k1 - 1; k >= k0; --k) {")
             if prefetched:
-                w("      const int kn = (k + 1 < k1) ? k + 1 : k;" if fwd else "      const int kn = (k - 1 >= k0) ? k - 1 : k;")
+                w(f"      const int kn = {ahead('k', D)};")
                 for key in prefetched:
                     w(f"      const {self._ctype(key)} n_{_tag(key)} = {self._load(key, 'kn')};")
             L.extend(body)
@@ -301,7 +311,9 @@ class ColumnKernel:
                     raise NotColumnable("carry chain")  # pragma: no cover
                 w(f"      r_{_tag(key)} = r_{_tag(src)};")
             for key in prefetched:
-                w(f"      r_{_tag(key)} = n_{_tag(key)};")
+                chain = [f"r_{_tag(key)}"] + [f"p{j}_{_tag(key)}" for j in range(1, D)] + [f"n_{_tag(key)}"]
+                for dst, src in zip(chain, chain[1:]):
+                    w(f"      {dst} = {src};")
             w("      }")
             w("    }")
             w("  }")

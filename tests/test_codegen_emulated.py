@@ -119,7 +119,7 @@ SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lo
 
 
 @pytest.mark.parametrize("name", SEQ_CASES)
-@pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_cache": False}])
+@pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"seq_cache": False}])
 def test_column_generator_variants(name, opts):
     """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
     baseline column kernel: same results on ragged domains, both lowerings"""
