@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 import hashlib
 import mmap
+import os
 import pathlib
 import struct
 import subprocess
@@ -23,6 +24,20 @@ from gt4py_b200 import codegen, ir as b2ir
 HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE.parent.parent / "gt4py_b200" / "csrc"
 BUILD = pathlib.Path(tempfile.gettempdir()) / "gt4py_b200_emu"
+
+
+def _runtime_object() -> pathlib.Path:
+    key = hashlib.sha256((HERE / "cuda_shim.h").read_bytes() + (HERE / "emu_runtime.cpp").read_bytes()).hexdigest()[:16]
+    obj = BUILD / f"emu_runtime_{key}.o"
+    if not obj.exists():
+        tmp = f"{obj}.{os.getpid()}.tmp"
+        cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-fPIC", "-c", "-DB200_HOST_EMU", "-I", str(HERE),
+               str(HERE / "emu_runtime.cpp"), "-o", tmp]  # fmt: skip
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("emulator runtime build failed:\n" + proc.stderr[-3000:])
+        os.replace(tmp, obj)
+    return obj
 
 
 def _align_up(v, a):
@@ -44,11 +59,14 @@ class EmuStencil:
         if not so.exists():
             src = BUILD / f"{codegen._cname(name)}_{key}.cpp"
             src.write_text(text)
-            cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DB200_HOST_EMU", "-ffp-contract=off",
-                   "-I", str(HERE), "-I", str(CSRC), "-x", "c++", str(src), str(HERE / "emu_runtime.cpp"), "-o", str(so)]
+            # the lockstep runtime (heavy <thread>/<barrier> headers) is compiled once; kernels at -O0:
+            # compile time dominates these tests, the domains are tiny
+            cmd = ["g++", "-std=c++20", "-O0", "-pthread", "-shared", "-fPIC", "-DB200_HOST_EMU", "-ffp-contract=off",
+                   "-I", str(HERE), "-I", str(CSRC), "-x", "c++", str(src), "-x", "none", str(_runtime_object()), "-o", str(so) + ".tmp"]
             proc = subprocess.run(cmd, capture_output=True, text=True)
             if proc.returncode != 0:
                 raise RuntimeError("emulator build failed:\n" + proc.stderr[-3000:])
+            os.replace(str(so) + ".tmp", so)
         self.lib = ctypes.CDLL(str(so))
         self.lib.emu_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint), ctypes.c_int]
         self.lib.emu_trace_read.restype = ctypes.c_longlong
