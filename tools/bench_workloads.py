@@ -1,0 +1,280 @@
+"""Benchmarks of the BASELINE.json configs other than the headline one (which is bench.py's):
+
+  --workload tridiagonal   config 3: K-tridiagonal solve 512x512x160 fp64, FORWARD+BACKWARD sweeps (no halo; N>1 = replicas)
+  --workload upwind5       config 4: 5th-order upwind advection 2048x2048x80 fp32, STRONG-scaled over N GPUs
+                           (J slabs of 2048/N rows, NCCL halo exchange of phi, width 3, every step)
+  --workload fastwaves     config 5: pressure-gradient -> divergence -> vertical implicit solve, 4096 x (512*N) x 80
+                           fp32, WEAK-scaled (4096x4096x80 per box of 8); exchanges pp before the pressure
+                           gradient and u, v before the divergence
+
+Same launch / timing / JSON conventions as bench.py (torchrun for N>1, W warm-up steps, exactly K timed
+steps between CUDA events, max over ranks, rank 0 prints one line with `roofline` and, at N=1,
+`cpu_baseline`).  `--plan` prints the workload description without touching a device (CPU-testable).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+from gt4py_b200 import testing  # noqa: E402
+
+
+def workload(name: str, n_gpus: int):
+    """-> dict(stencils=[(fixture, variant)], domain (per rank), halo (I,J,K), exchanges={stencil index: [(field, width)]},
+    scaling, label).  Fields of the same name are shared between the stencils of a step."""
+    if name == "tridiagonal":
+        return dict(stencils=[("tridiagonal_f64", "default")], domain=(512, 512, 160), halo=(0, 0, 0), exchanges={},
+                    scaling="weak", dtype="f64", label="K-tridiagonal solve 512x512x160 fp64 per GPU (BASELINE configs[2]); replicas, no exchange")  # fmt: skip
+    if name == "upwind5":
+        if 2048 % n_gpus:
+            raise SystemExit("upwind5: 2048 rows must divide by the number of GPUs")
+        return dict(stencils=[("upwind5_f32", "staged")], domain=(2048, 2048 // n_gpus, 80), halo=(3, 3, 0),
+                    exchanges={0: [("phi", 3)]}, scaling="strong", dtype="f32",
+                    label=f"5th-order upwind advection 2048x2048x80 fp32 (BASELINE configs[3]), J slabs of {2048 // n_gpus} rows")  # fmt: skip
+    if name == "fastwaves":
+        return dict(stencils=[("fw_pgrad_f32", "staged"), ("fw_div_f32", "staged"), ("fw_wsolve_f32", "default")],
+                    domain=(4096, 512, 80), halo=(1, 1, 1), exchanges={0: [("pp", 1)], 1: [("u", 1), ("v", 1)]},
+                    rename={0: {"u_out": "u", "v_out": "v"}, 2: {"pp_out": "pp_new"}}, scaling="weak", dtype="f32",
+                    label="fast-waves suite (pressure gradient, divergence, vertical implicit solve) 4096x512x80 fp32 per GPU "
+                          "(BASELINE configs[4]: 4096x4096x80 per box of 8)")  # fmt: skip
+    raise SystemExit(f"unknown workload {name}")
+
+
+def step_description(w):
+    """Per stencil: IR, argument binding (stencil parameter -> shared buffer name), bytes per cell."""
+    out = []
+    for n, (fixture, variant) in enumerate(w["stencils"]):
+        st = testing.load_ir(fixture, variant)
+        ren = w.get("rename", {}).get(n, {})
+        binding = {p["name"]: ren.get(p["name"], p["name"]) for p in st["params"] if p["t"] == "field"}
+        out.append(dict(fixture=fixture, variant=variant, ir=st, binding=binding, bytes_per_cell=testing.algorithmic_bytes_per_cell(st)))
+    return out
+
+
+def plan(name: str, n_gpus: int):
+    w = workload(name, n_gpus)
+    steps = step_description(w)
+    buffers = {}
+    for s in steps:
+        for p in s["ir"]["params"]:
+            if p["t"] == "field":
+                buffers.setdefault(s["binding"][p["name"]], p["dtype"])
+    return dict(workload=name, n_gpus=n_gpus, domain_per_gpu=w["domain"], halo=w["halo"], scaling=w["scaling"],
+                stencils=[s["fixture"] for s in steps], bytes_per_cell=[s["bytes_per_cell"] for s in steps],
+                buffers=buffers, exchanges={str(k): v for k, v in w["exchanges"].items()}, label=w["label"])  # fmt: skip
+
+
+def make_inputs(buffers, shape, rng):
+    data = {}
+    for name, dtype in buffers.items():
+        a = rng.random(shape).astype(dtype)
+        if name in ("diag", "rho"):
+            a += 1.0
+        if name in ("inf", "sup"):
+            a *= 0.1
+        if name == "hhl":  # monotone in K like a terrain-following height
+            a += 100.0 * np.arange(shape[2], 0, -1, dtype=a.dtype)[None, None, :]
+        data[name] = a.astype(dtype)
+    return data
+
+
+def default_params(st, fixture):
+    spec = testing.CASE_SPECS.get(fixture, {}).get("params", {})
+    out = {}
+    for p in st["params"]:
+        if p["t"] == "scalar" and st["parameter_info"].get(p["name"]) is not None:
+            v = spec.get(p["name"], 0.75 if p["dtype"].startswith("float") else 2)
+            out[p["name"]] = np.dtype(p["dtype"]).type(v)
+    return out
+
+
+def cpu_baseline(steps, halo, sample=(128, 128, 16)):
+    from oracle import numpy_oracle
+
+    rng = np.random.default_rng(0)
+    shape = tuple(sample[a] + 2 * halo[a] for a in range(3))
+    buffers = {}
+    for s in steps:
+        for p in s["ir"]["params"]:
+            if p["t"] == "field":
+                buffers.setdefault(s["binding"][p["name"]], p["dtype"])
+    data = make_inputs(buffers, shape, rng)
+
+    def one():
+        for s in steps:
+            fields = {p: data[b] for p, b in s["binding"].items()}
+            numpy_oracle.run(s["ir"], fields, default_params(s["ir"], s["fixture"]), sample, {p: tuple(halo) for p in fields})
+
+    one()
+    times = []
+    t_end = time.perf_counter() + 10.0
+    while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 30):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    cells = sample[0] * sample[1] * sample[2]
+    return {"value": round(cells / float(np.median(times)) / 1e6, 3), "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
+            "sample": f"oracle, {sample[0]}x{sample[1]}x{sample[2]} sub-domain, {len(times)} steps, median ({os.cpu_count()} host cores available, NumPy uses 1)"}  # fmt: skip
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", required=True, choices=["tridiagonal", "upwind5", "fastwaves"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--plan", action="store_true")
+    ap.add_argument("--options", default="{}", help="JSON code-generation options for every stencil")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.plan:
+        print(json.dumps(plan(args.workload, args.gpus)))
+        return
+
+    import torch
+
+    import bench as headline
+    from gt4py_b200 import runtime, storage
+    from gt4py_b200.distributed import HaloExchanger, SlabDecomposition
+    from gt4py_b200.stencil import B200Stencil
+
+    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device — the b200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w = workload(args.workload, world)
+    steps = step_description(w)
+    ni, nj, nk = w["domain"]
+    hi, hj, hk = w["halo"]
+    shape = (ni + 2 * hi, nj + 2 * hj, nk + 2 * hk)
+    origin3 = (hi, hj, hk)
+    buffers = {}
+    for s in steps:
+        for p in s["ir"]["params"]:
+            if p["t"] == "field":
+                buffers.setdefault(s["binding"][p["name"]], p["dtype"])
+    opts = {"device_sync": False, **json.loads(args.options)}
+    # two rotating buffer sets (working set >> L2)
+    rng = np.random.default_rng(rank)
+    sets = []
+    for _ in range(2):
+        host = make_inputs(buffers, shape, rng)
+        sets.append({n: storage.from_array(a, aligned_index=origin3) for n, a in host.items()})
+    frozen = []
+    for s in steps:
+        st = B200Stencil(s["ir"], opts, name=f"{s['fixture']}.{s['variant']}")
+        frozen.append((st.freeze(origin={p: origin3 for p in s["binding"]}, domain=(ni, nj, nk)), default_params(s["ir"], s["fixture"]), st))
+    exchanger = None
+    lib = runtime.load_library()
+    main_stream = torch.cuda.current_stream().cuda_stream
+    if world > 1 and w["exchanges"]:
+        import ctypes
+
+        exchanger = HaloExchanger(SlabDecomposition(world, rank, nj * world), nj)
+        ev = [ctypes.c_void_p(), ctypes.c_void_p()]
+        for e in ev:
+            runtime.check(lib.b200_event_create(ctypes.byref(e)))
+
+    def step(i, exchange=True):
+        bufs = sets[i & 1]
+        n = 0
+        for k, (s, (fr, params, _)) in enumerate(zip(steps, frozen)):
+            if exchange and exchanger is not None and k in w["exchanges"]:
+                runtime.check(lib.b200_event_record(ev[0], main_stream))
+                runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev[0]))
+                n += exchanger.exchange([(bufs[f], hj, h) for f, h in w["exchanges"][k]])
+                runtime.check(lib.b200_event_record(ev[1], exchanger.stream))
+                runtime.check(lib.b200_stream_wait_event(main_stream, ev[1]))
+            n += fr(**{p: bufs[b] for p, b in s["binding"].items()}, **params)
+        return n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = headline.ClockSampler(local_rank) if rank == 0 else None
+    if clocks is not None:
+        clocks.__enter__()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    for i in range(args.steps):
+        launches += step(i)
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    extra = int(min(2000, max(0, (600.0 - total_ms) / max(total_ms / args.steps, 1e-3))))
+    for j in range(extra):  # same count on every rank (derived from the all-reduced time): matched exchanges
+        step(j)
+    barrier()
+    if clocks is not None:
+        clocks.__exit__(None, None, None)
+    ms = total_ms / args.steps
+    cells = ni * nj * nk * world
+    # kernels only, back to back (no exchange): the roofline numerator
+    kt = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            step(i, exchange=False)
+        b.record()
+        b.synchronize()
+        kt.append(a.elapsed_time(b) / 10)
+    kernel_ms = float(np.mean(kt))
+    bpc = sum(s["bytes_per_cell"] for s in steps)
+    peak, peak_src = headline.measured_peaks()
+    achieved = ni * nj * nk * bpc / kernel_ms / 1e6
+    if rank == 0:
+        line = {
+            "metric": f"Mcell-updates/s + achieved HBM GB/s, {args.workload}",
+            "value": round(cells / ms / 1e3, 1), "unit": "Mcell-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": w["dtype"],
+            "data": "synthetic",
+            "config": {"workload": w["label"], "domain_per_gpu": [ni, nj, nk], "halo": list(w["halo"]),
+                       "stencils": [s["fixture"] for s in steps], "codegen_options": opts,
+                       "kernels": [st.compiled.kernel_names() for _, _, st in frozen],
+                       "l2": "two rotating buffer sets, each larger than the 126 MB L2"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": round(kernel_ms, 5),
+                         "algorithmic_bytes_per_launch": ni * nj * nk * bpc, "bytes_per_cell": bpc},
+            "clocks": clocks.summary() if clocks is not None else None,
+        }  # fmt: skip
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(steps, w["halo"])
+        print(json.dumps(line))
+    if exchanger is not None:
+        exchanger.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
