@@ -70,16 +70,20 @@ class StreamKernel:
         self.vmap: Dict[Tuple, Value] = {}
         self.cur: Dict[str, Value] = {}
         self.stage_of_stmt: List = []
+        self.direct: set = set()  # K-only fields read with uniform loads
         self.nstages = len(hes)
 
     # ---- eligibility + value discovery (pass 1) --------------------------------------------------
     def _decl(self, name: str) -> dict:
         return self.ft.entries[self.ft.index[name]]
 
-    def _check_field(self, name: str):
+    def _check_field(self, name: str, *, write: bool = False):
         d = self._decl(name)
-        if not all(d["dims"]) or d["data_dims"]:
-            raise NotStreamable(f"field {name} is not a plain IJK field")
+        if d["data_dims"]:
+            raise NotStreamable(f"field {name} has data dimensions")
+        # a read-only IJ field streams like an IJK field whose K stride is 0; everything else must be IJK
+        if not (all(d["dims"]) or (not write and d["dims"][0] and d["dims"][1])):
+            raise NotStreamable(f"field {name} is not an IJK (or read-only IJ) field")
         if b2ir.ITEMSIZE[d["dtype"]] not in (4, 8):
             raise NotStreamable(f"field {name}: itemsize")
 
@@ -93,7 +97,7 @@ class StreamKernel:
         return self.vmap[key]
 
     def _new_version(self, name: str, stage: int) -> Value:
-        self._check_field(name)
+        self._check_field(name, write=True)
         n = sum(1 for v in self.values if v.kind == "tmp" and v.field == name)
         v = Value("tmp", name, self._decl(name)["dtype"], ver=n, stage=stage)
         self.vmap[("tmp", name, n)] = v
@@ -106,6 +110,12 @@ class StreamKernel:
             raise NotStreamable("variable/absolute K offset or data index")
         di, dj, dk = off
         name = node["name"]
+        d0 = self._decl(name)
+        if not d0["dims"][0] and not d0["dims"][1] and not d0["data_dims"] and d0["kind"] == "api":
+            # K-only (or 0-d) field: one value per level, the same for the whole warp -> plain uniform
+            # load in the expression (read-only path), not a row stream
+            self.direct.add(name)
+            return "direct", 0, 0
         if name in self.cur:
             if dk != 0:
                 raise NotStreamable("K-offset read of a field written in the same block")
@@ -129,7 +139,7 @@ class StreamKernel:
                 if t == "field":
                     v, di, dj = self._resolve_read(n, stage)
                     self.binding[id(n)] = (v, di, dj)
-                    if v is not None:
+                    if v is not None and v != "direct":
                         v.reads.append((stage, di, dj))
                 elif t == "iter" and n["axis"] not in ("I", "J", "K"):
                     raise NotStreamable("iterator")
@@ -491,7 +501,7 @@ class StreamKernel:
         w("  }")
         w("}")
         gen.src.append("\n".join(L))
-        gen.live |= {v.field for v in self.values if v.kind == "in" or v.store}
+        gen.live |= {v.field for v in self.values if v.kind == "in" or v.store} | self.direct
         gen.kernels.append(
             {
                 "name": name, "kind": "stream", "block": [32, self.NW, 1], "tile": [self.SQ * V, self.TJ, V],
@@ -617,6 +627,8 @@ class StreamKernel:
                 v, di, dj = kern.binding[id(node)]
                 if v is None:
                     return f"(({CT[node['dtype']]})0)"
+                if v == "direct":
+                    return cg.ExprGen.field_load(self, node)
                 slot = kern._slot_of(v, kern.lag[si], dj, phase)
                 e = self.elem + di
                 if 0 <= e < V:
@@ -788,21 +800,139 @@ def _vec_store(ct: str, V: int, regs: List[str], addr: str) -> str:
 
 
 # ---------------------------------------------------------------------------------------------------
+# loop fusion (interval refinement) — consecutive PARALLEL computations become one set of kernels
+# ---------------------------------------------------------------------------------------------------
+def _bkey(b) -> Tuple[int, int]:
+    return (0, int(b[1])) if b[0] == "start" else (1, int(b[1]))
+
+
+def _loop_accesses(loop):
+    acc = [a for sec in loop["sections"] for he in sec["hes"] for a in b2ir.field_accesses(he["body"])]
+    written = {a["name"] for a in acc if a["write"]}
+    reads_off = {a["name"] for a in acc if not a["write"] and (isinstance(a["off"], dict) or tuple(a["off"]) != (0, 0, 0))}
+    reads_koff = {a["name"] for a in acc if not a["write"] and (isinstance(a["off"], dict) or a["off"][2] != 0)}
+    return written, reads_off, reads_koff
+
+
+def _can_fuse(a, b, stencil) -> bool:
+    """Loop `b` may run level by level right behind loop `a` (inside one kernel per K interval) when
+    no value crosses levels or threads between them through memory: b reads nothing a writes at a K
+    offset (that level may not be computed yet), a reads nothing b writes at any offset (it may
+    already be overwritten), and the symbolic interval bounds of both are ordered for every domain
+    the stencil accepts (start+x <= end+y for all bounds, guaranteed by domain_info.min_k)."""
+    wa, ra_off, _ = _loop_accesses(a)
+    wb, _, rb_koff = _loop_accesses(b)
+    if wa & rb_koff or wb & ra_off:
+        return False
+    bounds = [bd for lp in (a, b) for sec in lp["sections"] for bd in sec["interval"]]
+    starts = [bd[1] for bd in bounds if bd[0] == "start"]
+    ends = [bd[1] for bd in bounds if bd[0] == "end"]
+    min_k = int(stencil["domain_info"]["min_k"])
+    if starts and ends and max(starts) - min(ends) > min_k:
+        return False
+    return True
+
+
+def _fuse(a, b):
+    bounds = sorted({_bkey(bd) for lp in (a, b) for sec in lp["sections"] for bd in sec["interval"]})
+    unkey = lambda k: ["start" if k[0] == 0 else "end", k[1]]  # noqa: E731
+    sections = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        hes = []
+        for lp in (a, b):
+            for sec in lp["sections"]:
+                if _bkey(sec["interval"][0]) <= lo and hi <= _bkey(sec["interval"][1]):
+                    hes += sec["hes"]
+        if hes:
+            sections.append({"interval": [unkey(lo), unkey(hi)], "hes": hes})
+    return {"order": "parallel", "sections": sections, "caches": [], "fused": True}
+
+
+def fuse_parallel_loops(stencil: Dict[str, Any]) -> Dict[str, Any]:
+    """Merge consecutive PARALLEL loops whenever `_can_fuse` holds: the K axis is cut at every
+    interval bound of either loop and each piece runs the horizontal executions of both, so values
+    handed from one computation to the next stay in the register windows of the streaming kernel
+    instead of a round trip through scratch memory (the reference reaches the same effect by
+    inlining the producer, gtc/passes/oir_optimizations/inlining.py OnTheFlyMerging, which this
+    backend skips because recomputation at every offset costs more than a window row)."""
+    out: List[dict] = []
+    changed = False
+    for loop in stencil["loops"]:
+        if out and loop["order"] == "parallel" and out[-1]["order"] == "parallel" and _can_fuse(out[-1], loop, stencil):
+            out[-1] = _fuse(out[-1], loop)
+            changed = True
+        else:
+            out.append(loop)
+    if not changed:
+        return stencil
+    new = dict(stencil)
+    new["loops"] = out
+    return new
+
+
+# ---------------------------------------------------------------------------------------------------
 # driver
 # ---------------------------------------------------------------------------------------------------
 def _fields_touched(hes) -> set:
     return {a["name"] for he in hes for a in b2ir.field_accesses(he["body"])}
 
 
-def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
-    """Generate with streaming kernels for every PARALLEL section that fits the template; other
-    loops use the point generator.  Returns None when nothing is streamable."""
+def _defined_before_use(hes, name: str) -> bool:
+    """Within this section, `name` is assigned unconditionally before any read and only read at K
+    offset 0: nothing flows into the section through it."""
+    defined = False
+
+    def reads(node, found):
+        b2ir.walk_exprs(node, lambda e: e["t"] == "field" and e["name"] == name and found.append(e))
+
+    def visit(stmts, top):
+        nonlocal defined
+        for st in stmts:
+            t = st["t"]
+            if t == "assign":
+                found: list = []
+                reads(st["right"], found)
+                left = st["left"]
+                if left["t"] == "field":
+                    for ix in left.get("data_index", []):
+                        reads(ix, found)
+                for e in found:
+                    if not defined or isinstance(e["off"], dict) or e["off"][2] != 0:
+                        return False
+                if left["t"] == "field" and left["name"] == name:
+                    if top:
+                        defined = True
+                    elif not defined:
+                        return False  # first definition under a mask: the old value survives
+            else:
+                found = []
+                reads(st.get("mask", st.get("cond", [])), found)
+                for e in found:
+                    if not defined or isinstance(e["off"], dict) or e["off"][2] != 0:
+                        return False
+                if visit(st["body"], False) is False:
+                    return False
+        return True
+
+    for he in hes:
+        if visit(he["body"], True) is False:
+            return False
+    return True
+
+
+def _generate(stencil: Dict[str, Any], options: Dict[str, Any], *, strict: bool):
     gen = cg.Generator(stencil, options)
     used_stream = False
     # fields touched per (loop, section) to decide which temporaries are kernel-local
     secs = [(li, si) for li, loop in enumerate(stencil["loops"]) for si, _ in enumerate(loop["sections"])]
     touched = {(li, si): _fields_touched(stencil["loops"][li]["sections"][si]["hes"]) for li, si in secs}
     temps = {t["name"] for t in stencil["temporaries"]}
+    # a temporary that every section (re)defines before using it never carries a value between kernels
+    private = {
+        t for t in temps
+        if all(_defined_before_use(stencil["loops"][li]["sections"][si]["hes"], t) for (li, si) in secs if t in touched[(li, si)])
+        and all(stencil["loops"][li]["order"] == "parallel" for (li, si) in secs if t in touched[(li, si)])
+    }  # fmt: skip
     for li, loop in enumerate(stencil["loops"]):
         if loop["order"] != "parallel":
             gen.lower_loop(loop)
@@ -811,7 +941,7 @@ def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
         ok = True
         for si, sec in enumerate(loop["sections"]):
             others = set().union(*[f for key, f in touched.items() if key != (li, si)]) if len(touched) > 1 else set()
-            global_fields = temps & others
+            global_fields = (temps & others) - private
             sk = StreamKernel(gen, sec["interval"], sec["hes"], global_fields, options)
             try:
                 sk.analyse()
@@ -820,6 +950,8 @@ def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
                 break
             plans.append(sk)
         if not ok:
+            if strict and loop.get("fused"):
+                return None  # a fused loop must stream; otherwise generate from the unfused stencil
             gen.lower_loop(loop)
             continue
         for sk in plans:
@@ -829,3 +961,15 @@ def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
     if not used_stream:
         return None
     return gen.finish()
+
+
+def try_generate(stencil: Dict[str, Any], options: Dict[str, Any]):
+    """Generate with streaming kernels for every PARALLEL section that fits the template; other
+    loops use the point generator.  Returns None when nothing is streamable."""
+    if options.get("fuse_loops", True):
+        fused = fuse_parallel_loops(stencil)
+        if fused is not stencil:
+            res = _generate(fused, options, strict=True)
+            if res is not None:
+                return res
+    return _generate(stencil, options, strict=False)

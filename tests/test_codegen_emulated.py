@@ -77,7 +77,8 @@ def test_point_generator_on_default_lowering(name):
     run_emulated(name, "default", {"strategy": "point"}, seed=1, check_golden=True)
 
 
-@pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32", "regions_f64"])
+@pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32", "regions_f64",
+                                  "fuse_chain_f32", "fuse_reuse_f64", "fuse_partial_f64"])  # fmt: skip
 @pytest.mark.parametrize("domain", [(1, 1, 1), (3, 2, 1), (61, 5, 2), (129, 70, 2)])
 def test_ragged_domains_streaming(name, domain):
     run_emulated(name, "staged", {"strategy": "auto"}, domain=domain, seed=2)
@@ -141,3 +142,21 @@ def test_column_generator_keeps_the_k_dataflow_in_registers():
     assert loop.count("b200::ldro<double>") == 2 and loop.count("= c_sup[") == 1 and loop.count("= c_rhs[") == 1
     assert loop.count("c_sup[(long long)k *") == 1 and loop.count("c_rhs[(long long)k *") == 1  # one store each
     assert "(k + (-1))" not in loop
+
+
+@pytest.mark.parametrize("name", ["fw_pgrad_f32", "fuse_chain_f32", "fuse_reuse_f64", "fuse_partial_f64", "tmp_koffset_f64", "k_intervals_f64"])
+def test_loop_fusion_by_interval_refinement(name):
+    """consecutive PARALLEL computations fused into one set of kernels (one per K interval piece) give
+    the results of the unfused stencil; values handed between them no longer go through scratch"""
+    from gt4py_b200 import codegen
+
+    st = testing.load_ir(name, "staged")
+    fused, plain = codegen.generate(st, {})[1], codegen.generate(st, {"fuse_loops": False})[1]
+    nk = lambda p: len(p["kernels"])  # noqa: E731
+    scratch = lambda p: {f["name"] for f in p["fields"] if f["kind"] == "temp"}  # noqa: E731
+    expect = {"fw_pgrad_f32": (4, 3, set()), "fuse_chain_f32": (6, 3, set()), "fuse_reuse_f64": (4, 2, {"t", "u"}),
+              "fuse_partial_f64": (5, 3, {"t"}), "tmp_koffset_f64": (4, 4, {"t"}), "k_intervals_f64": (3, 3, set())}[name]  # fmt: skip
+    assert (nk(plain), nk(fused), scratch(fused)) == expect
+    for opts in ({}, {"fuse_loops": False}, {"interior_loop": True, "static_pitch": 160}):
+        run_emulated(name, "staged", opts, domain=(139, 70, 4), seed=13, layout="b200", guard="end")
+        run_emulated(name, "default", opts, domain=(21, 9, 3), seed=14)

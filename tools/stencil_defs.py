@@ -597,3 +597,58 @@ def col_multiwrite_f32(a: F32, b: F32, *, w: np.float32):
             if t > 1.0:
                 b = b + t[0, 0, -1]
             t = t - 0.125
+
+
+# ---------------------------------------------------------------------------------------------
+# Several PARALLEL computations in one stencil: loop fusion by interval refinement (codegen_stream.py)
+# ---------------------------------------------------------------------------------------------
+@case("fuse_chain_f32", build={"literal_float_precision": 32})
+def fuse_chain_f32(a: F32, b: F32, c: F32):
+    # three computations with different vertical intervals; t and b are handed on at IJ offsets
+    with computation(PARALLEL), interval(...):
+        t = a[1, 0, 0] - a[0, 0, 0]
+    with computation(PARALLEL):
+        with interval(0, 1):
+            s = t[0, 0, 0] * 2.0
+        with interval(1, None):
+            s = t[0, 1, 0] + a[0, 0, -1]
+    with computation(PARALLEL):
+        with interval(0, -1):
+            c = s[0, 0, 0] + t[-1, 0, 0] + s[0, -1, 0]
+        with interval(-1, None):
+            c = s[1, 0, 0] - t[0, 0, 0]
+    with computation(PARALLEL), interval(...):
+        b = c[0, 0, 0] * 0.5 + s[0, 0, 0]
+
+
+@case("fuse_reuse_f64")
+def fuse_reuse_f64(a: F64, b: F64):
+    # a temporary that is redefined by a later computation after being read at an offset, and a
+    # masked redefinition in between
+    with computation(PARALLEL), interval(...):
+        t = a * 3.0
+    with computation(PARALLEL), interval(...):
+        u = t[1, 0, 0] + t[0, -1, 0]
+    with computation(PARALLEL), interval(...):
+        if a > 0.5:
+            t = u * 2.0
+    with computation(PARALLEL), interval(...):
+        b = t[0, 0, 0] + u[0, 1, 0] - t[-1, 0, 0]
+
+
+@case("fuse_partial_f64")
+def fuse_partial_f64(a: F64, b: F64, c: F64):
+    # the second computation reads the first one's result at a K offset (no fusion there), the third
+    # and fourth can be fused with each other
+    with computation(PARALLEL), interval(...):
+        t = a + 1.0
+    with computation(PARALLEL):
+        with interval(0, 1):
+            u = t[0, 0, 1]
+        with interval(1, None):
+            u = t[0, 0, -1] + t[0, 0, 0]
+    with computation(PARALLEL), interval(...):
+        v = u[1, 0, 0] * t[0, 1, 0]
+    with computation(PARALLEL), interval(...):
+        b = v[0, -1, 0] + u[0, 0, 0]
+        c = v[-1, 0, 0]
