@@ -237,7 +237,7 @@ class B200Backend(BaseBackend):
         "l2_prefetch": {"versioning": True, "type": int},
         "seq_cache": {"versioning": True, "type": bool},
         "seq_prefetch": {"versioning": True, "type": bool},
-        "interior_loop": {"versioning": True, "type": bool},
+        "interior_loop": {"versioning": True, "type": object},  # True | "steady"
         "static_pitch": {"versioning": True, "type": int},
         "specialize": {"versioning": True, "type": str},  # "off" | "lazy": per-pitch kernels at first call
         "verbose": {"versioning": False, "type": bool},

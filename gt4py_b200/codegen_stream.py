@@ -434,21 +434,8 @@ class StreamKernel:
         n_pro = a - t_first
         w(f"  int t = T_lo + ({t_first});")
         w(f"  const int t_end = T_hi + ({t_last});   // exclusive")
-        # prologue: general steps until the steady state starts (compile-time count)
-        for n in range(n_pro):
-            w(f"  if (t < t_end) {{  // prologue step {n}")
-            w("      const int tt = t;")
-            L.extend(self._emit_step(n % U, fast=False))
-            w("  }")
-            w("  ++t;")
-        ph0 = n_pro % U
-        # steady state: U fast steps per trip, running row pointers
-        for v in self.values:
-            if v.kind == "in" or v.store:
-                ct = CT[v.dtype]
-                const = "const " if v.kind == "in" else ""
-                w(f"  {const}{ct}* q_{v.cname} = p_{v.cname} + (long long)(t - ({v.lag})) * sj_{v.cname} + g0;")
         streams = [v for v in self.values if v.kind == "in" or v.store]
+        ph0 = n_pro % U
         # static pitch: the row pitch (J stride, in elements) of every streamed field is a compile-time
         # constant -> row addresses inside a trip are immediates off ONE running pointer per stream
         # (no per-step 64-bit address arithmetic); checked at run time, other pitches take the general loop
@@ -458,27 +445,14 @@ class StreamKernel:
             w(f"  constexpr long long SJ = {self.SJ};")
             w("  const bool spitch = " + " && ".join(f"sj_{v.cname} == SJ" for v in streams) + ";")
             pitch_ok = " && spitch"
-        modes = [("pure", "allvec && wpure" + pitch_ok, f"T_hi + ({b})")]
-        if not self.opts.get("pure_loop", True):
-            modes = [("fastall", "allvec" + pitch_ok, f"T_hi + ({b})")]  # one steady loop for all warps, uniform branch per load
-        # a second steady loop for warps that do hold partially valid vectors costs ~18 registers
-        # (72 -> 90 for horizontal diffusion); by default those few edge warps use the general loop
-        if self.opts.get("edge_loop", False) and self.opts.get("pure_loop", True):
-            modes.append(("fast", "allvec && !wpure" + pitch_ok, f"T_hi + ({b})"))
-        # interior loop: warps whose 32 lanes all hold fully valid vectors of every stream (all but the
-        # last I segment of a row) need no per-lane load predicates at all, and run only the trips in
-        # which every L2 prefetch is allowed; what is left of the tile falls through to the loops below
-        if self.opts.get("interior_loop", False) and self.opts.get("pure_loop", True) and not any(self.row_guard.values()):
-            w("  const bool winterior = __all_sync(0xffffffffu, " + " && ".join(
-                f"full_{v.cname}" if v.kind == "in" else f"(!own || full_{v.cname})" for v in streams) + ");")
-            lim = [f"T_hi + ({b})"] + ([f"pfe_{v.cname}" for v in self.values if v.kind == "in"] if pfd > 0 else [])
-            w("  int t_int = " + lim[0] + ";")
-            for x in lim[1:]:
-                w(f"  t_int = t_int < {x} ? t_int : {x};")
-            if pfd > 0:
-                w("  const bool pf_lane = (lane & 3) == 0;")
-            modes.insert(0, ("interior", "allvec && wpure && winterior" + pitch_ok, "t_int"))
-        for mode, cond, bound in modes:
+
+        def running_pointers():
+            for v in streams:
+                ct = CT[v.dtype]
+                const = "const " if v.kind == "in" else ""
+                w(f"  {const}{ct}* q_{v.cname} = p_{v.cname} + (long long)(t - ({v.lag})) * sj_{v.cname} + g0;")
+
+        def steady_loop(mode, cond, bound):
             w(f"  if ({cond}) for (; t + {U} <= {bound}; t += {U}) {{   // steady loop ({mode})")
             w(f"    B200_TRACE({3 if mode == 'interior' else (0 if mode == 'pure' else 1)});")
             for u in range(U):
@@ -490,15 +464,66 @@ class StreamKernel:
                 for v in streams:
                     w(f"    q_{v.cname} += {U} * SJ;")
             w("  }")
-        # tail: remaining steady rows + epilogue, general steps, same phase sequence
-        w(f"  for (; t < t_end; t += {U}) {{")
-        for u in range(U):
-            w(f"    if (t + {u} < t_end) {{  // tail step, rotation phase {(ph0 + u) % U}")
-            w("      B200_TRACE(2);")
-            w(f"      const int tt = t + {u};")
-            L.extend(self._emit_step((ph0 + u) % U, fast=False))
-            w("    }")
-        w("  }")
+
+        def prologue(fast):
+            # steps until the steady state starts (compile-time count)
+            for n in range(n_pro):
+                w(f"  if (t < t_end) {{  // prologue step {n}")
+                w("      const int tt = t;")
+                L.extend(self._emit_step(n % U, fast=fast))
+                w("  }")
+                w("  ++t;")
+
+        def tail(fast):
+            # remaining steady rows + epilogue, same phase sequence
+            w(f"  for (; t < t_end; t += {U}) {{")
+            for u in range(U):
+                w(f"    if (t + {u} < t_end) {{  // tail step, rotation phase {(ph0 + u) % U}")
+                w(f"      B200_TRACE({4 if fast else 2});")
+                w(f"      const int tt = t + {u};")
+                L.extend(self._emit_step((ph0 + u) % U, fast=fast))
+                w("    }")
+            w("  }")
+
+        # interior warps: all 32 lanes hold fully valid vectors of every stream (all but the last I
+        # segment of a row) and every row the tile needs exists -> the WHOLE march runs without
+        # per-lane predicates: prologue / epilogue steps only test warp-uniform row ranges, steady
+        # trips have unconditional loads and run while every L2 prefetch is allowed
+        interior = self.opts.get("interior_loop", False) and self.opts.get("pure_loop", True) and not any(self.row_guard.values())
+        # interior_loop="steady": only the steady trips of interior warps are specialised (fewer registers)
+        steady_only = interior and self.opts.get("interior_loop") == "steady"
+        if interior:
+            w("  const bool winterior = __all_sync(0xffffffffu, " + " && ".join(
+                f"full_{v.cname}" if v.kind == "in" else f"(!own || full_{v.cname})" for v in streams) + ");")
+            lim = [f"T_hi + ({b})"] + ([f"pfe_{v.cname}" for v in self.values if v.kind == "in"] if pfd > 0 else [])
+            w("  int t_int = " + lim[0] + ";")
+            for x in lim[1:]:
+                w(f"  t_int = t_int < {x} ? t_int : {x};")
+            if pfd > 0:
+                w("  const bool pf_lane = (lane & 3) == 0;")
+        if interior and not steady_only:
+            w(f"  if (allvec && wpure && winterior{pitch_ok}) {{")
+            prologue("igeneral")
+            running_pointers()
+            steady_loop("interior", "true", "t_int")
+            tail("igeneral")
+            w("  } else {")
+        prologue(False)
+        running_pointers()
+        modes = [("pure", "allvec && wpure" + pitch_ok, f"T_hi + ({b})")]
+        if steady_only:
+            modes.insert(0, ("interior", "allvec && wpure && winterior" + pitch_ok, "t_int"))
+        if not self.opts.get("pure_loop", True):
+            modes = [("fastall", "allvec" + pitch_ok, f"T_hi + ({b})")]  # one steady loop for all warps, uniform branch per load
+        # a second steady loop for warps that do hold partially valid vectors costs ~18 registers
+        # (72 -> 90 for horizontal diffusion); by default those few edge warps use the general loop
+        if self.opts.get("edge_loop", False) and self.opts.get("pure_loop", True):
+            modes.append(("fast", "allvec && !wpure" + pitch_ok, f"T_hi + ({b})"))
+        for mode, cond, bound in modes:
+            steady_loop(mode, cond, bound)
+        tail(False)
+        if interior and not steady_only:
+            w("  }")
         w("}")
         gen.src.append("\n".join(L))
         gen.live |= {v.field for v in self.values if v.kind == "in" or v.store} | self.direct
@@ -532,7 +557,7 @@ class StreamKernel:
             ro = v.field not in self.written
             regs = [self.reg(v, slot, e) for e in range(V)]
             ldf = "__ldg" if ro else "*"
-            if fast:
+            if fast and fast != "igeneral":
                 guard = f"R >= rlo_{c} && R < rhi_{c}" if self.row_guard[c] else ""
                 L.append(f"{ind}{{")
                 if guard:
@@ -577,6 +602,13 @@ class StreamKernel:
                         L.append(f"{ind}  if (pfl_{c} && tt < pfe_{c}) b200::prefetch_l2({pfa});")
                 if not self.SJ:
                     L.append(f"{ind}  q_{c} += sj_{c};")
+                L.append(f"{ind}}}")
+                continue
+            if fast == "igeneral":
+                # interior warp outside the steady state: only the (warp-uniform) row range decides
+                pitch = "SJ" if self.SJ else f"sj_{c}"
+                L.append(f"{ind}{{ const int R = tt - ({v.lag});")
+                L.append(f"{ind}  if (R >= T_lo + ({v.nj[0]}) && R < T_hi + ({v.nj[1]})) {_vec_load(ct, V, regs, f'p_{c} + (long long)R * {pitch} + g0', ro)}")
                 L.append(f"{ind}}}")
                 continue
             L.append(f"{ind}{{ const int R = tt - ({v.lag});")
@@ -733,6 +765,9 @@ class StreamKernel:
         regs = [self.reg(v, slot, x) for x in range(V)]
         ct = CT[v.dtype]
         rowg = f"r >= A.g.j_lo + ({e[1][0]}) && r < A.g.j_hi + ({e[1][1]})"
+        if fast == "igeneral":
+            pitch = "SJ" if self.SJ else f"sj_{c}"
+            return [f"{ind}if (own && r >= T_lo && r < T_hi) {_vec_store(ct, V, regs, f'p_{c} + (long long)r * {pitch} + g0')}"]
         if fast:
             g = f"{rowg} && " if self.row_guard[c] else ""
             qa = self._row_addr(c)

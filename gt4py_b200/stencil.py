@@ -322,7 +322,13 @@ class B200Stencil:
         {"interior_loop": True, "static_pitch": "auto", "prefetch": 0},
         {"interior_loop": True, "static_pitch": "auto", "vector_width": 4},
         {"interior_loop": True, "static_pitch": "auto", "vector_width": 4, "prefetch": 0},
+        {"interior_loop": "steady", "static_pitch": "auto"},
+        {"interior_loop": True, "static_pitch": "auto", "tile_j": 52},
+        {"interior_loop": True, "static_pitch": "auto", "tile_j": 96},
+        {"interior_loop": True, "static_pitch": "auto", "min_blocks": 8},
+        {"interior_loop": True, "static_pitch": "auto", "min_blocks": 8, "tile_j": 128},
         {"interior_loop": True, "static_pitch": "auto", "min_blocks": 9},
+        {"interior_loop": True, "static_pitch": "auto", "tile_j": 256},
         {"edge_loop": True},
         {"pure_loop": False},
         {"vector_width": 4},

@@ -75,8 +75,8 @@ class EmuStencil:
 
     def trace(self, reset=True):
         """B200_TRACE counters: {0: steady-loop trips (pure), 1: steady-loop trips (edge/fastall),
-        2: general march steps, 3: steady-loop trips (interior)} of the streaming kernels since the last reset."""
-        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(4)}
+        2: general march steps, 3: steady-loop trips (interior), 4: interior prologue/epilogue steps} of the streaming kernels since the last reset."""
+        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(5)}
 
     # ---- mirror of launcher.cu ------------------------------------------------------------------
     def _temp_layout(self, f, dom):

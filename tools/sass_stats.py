@@ -44,7 +44,9 @@ def analyze(name, opts, variant="staged", show=False):
     return out
 TABLE = [
     ("hdiff_f32", {}), ("hdiff_f32", {"static_pitch": 1056}), ("hdiff_f32", {"interior_loop": True}),
+    ("hdiff_f32", {"interior_loop": "steady", "static_pitch": 1056}),
     ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056}),
+    ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056, "min_blocks": 8}),
     ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056, "vector_width": 4}),
     ("upwind5_f32", {}), ("upwind5_f32", {"interior_loop": True, "static_pitch": 2080}),
     ("tridiagonal_f64", {"seq_cache": False}), ("tridiagonal_f64", {}),
