@@ -200,11 +200,16 @@ def main():
     wd = threading.Timer(args.watchdog, _abort)
     wd.daemon = True
     wd.start()
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        wd.cancel()
 
-    if args.impl == "reference":
-        run_reference(args)
-        return
 
+def run_b200(args):
     import torch
 
     from gt4py_b200 import runtime, storage, testing
@@ -248,8 +253,12 @@ def main():
             host_in, host_coeff = h_in, h_co
     tuned = None
     if not args.no_autotune:
-        # pick the fastest code-generation variant for this stencil x domain on this device
-        tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
+        # pick the fastest code-generation variant for this stencil x domain on this device (every
+        # candidate is checked bit-for-bit against the default variant before it is timed)
+        try:
+            tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
+        except Exception as exc:  # keep the measured default rather than lose the bench line
+            tuned = f"autotune failed, default options used: {type(exc).__name__}: {exc}"
     frozen = stencil.freeze(origin=origins, domain=domain)
 
     exchanger = None

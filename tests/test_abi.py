@@ -75,3 +75,60 @@ def test_lazy_pitch_specialisation_selects_one_variant_per_pitch():
     assert runtime.CompiledStencil(st, {}).specialized_for(descs(64)).options.get("static_pitch") is None
     col = runtime.CompiledStencil(testing.load_ir("tridiagonal_f64"), {"specialize": "lazy"})
     assert not col._special and all(k["kind"] != "stream" for k in col.plan["kernels"])
+
+
+def test_autotune_control_flow_with_a_stubbed_device(monkeypatch):
+    """bench.py runs B200Stencil.autotune on its main path: exercise its control flow here (candidate
+    resolution incl. static_pitch="auto", de-duplication, parity check against the first candidate,
+    rejection of a candidate that writes something else, selection) with launches and CUDA events stubbed."""
+    import numpy as np
+    import torch
+
+    from gt4py_b200 import storage, testing
+    from gt4py_b200.stencil import B200Stencil
+
+    st = testing.load_ir("hdiff_f32", "staged")
+    shape, org = (40, 24, 3), (2, 2, 0)
+
+    def dev(fill):
+        es, total, lead = storage.compute_layout(shape, storage.layout_map(("I", "J", "K")), 4, 32, org)
+        return storage.DeviceArray(torch.full((total + lead,), fill, dtype=torch.float32), lead, shape, es, np.float32)
+
+    fields = {"in_field": dev(1.0), "coeff": dev(0.5), "out_field": dev(0.0)}
+    calls = []
+
+    def fake_run(self, descs, scalars, domain, *, stream=None, subbox=None):
+        calls.append(dict(self.options))
+        bad = self.options.get("tile_j") == 32  # this variant "computes" something else
+        fields["out_field"].torch().fill_(7.0 if not bad else 8.0)
+        return 1
+
+    class FakeEvent:
+        t = 0.0
+
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            FakeEvent.t += 1.0
+            self.at = FakeEvent.t
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            # pretend the static-pitch interior variant is the fastest
+            last = calls[-1]
+            return 1.0 if (last.get("interior_loop") is True and last.get("static_pitch") and len(last) == 3) else 2.0 + len(last)
+
+    monkeypatch.setattr(runtime.CompiledStencil, "run_descs", fake_run)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    stencil = B200Stencil(st, {"device_sync": False})
+    cands = [{}, {"static_pitch": "auto"}, {"interior_loop": True, "static_pitch": "auto"}, {"tile_j": 32}, {"tile_j": 64}]
+    tuned = stencil.autotune(fields, {}, domain=(36, 20, 3), origin={n: org for n in fields}, candidates=cands, iters=2)
+    assert stencil.tune_rejected == [{"tile_j": 32}]
+    assert tuned[0][0] == {"interior_loop": True, "static_pitch": 64} and stencil.backend_options["static_pitch"] == 64
+    assert [c for c, _ in tuned].count({"tile_j": 64}) == 0  # same source as the default: de-duplicated
+    assert len(tuned) == 3
+    json_ok = __import__("json").dumps({"autotune": tuned, "options": stencil.backend_options})
+    assert "static_pitch" in json_ok

@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--plan", action="store_true")
     ap.add_argument("--options", default="{}", help="JSON code-generation options for every stencil")
+    ap.add_argument("--shrink", type=int, default=1, help="divide the horizontal domain by this factor (smoke runs only)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,6 +162,9 @@ def main():
     w = workload(args.workload, world)
     steps = step_description(w)
     ni, nj, nk = w["domain"]
+    if args.shrink > 1:
+        ni, nj = max(8, ni // args.shrink), max(8, nj // args.shrink)
+        w["label"] += f" [SMOKE RUN: horizontal domain shrunk to {ni}x{nj}]"
     hi, hj, hk = w["halo"]
     shape = (ni + 2 * hi, nj + 2 * hj, nk + 2 * hk)
     origin3 = (hi, hj, hk)
