@@ -2,7 +2,7 @@
 # Run the REFERENCE's own cartesian test-suites against the b200 code generator on the CPU emulator
 # (test-only backend "b200emu", tests/emu/emu_backend.py).  Build container only (needs /root/reference).
 #   tools/run_reference_tests.sh            -> test_code_generation.py + test_suites.py + feature_tests/
-#                                              + test_math_functions.py (≈7 min; 191 tests on b200emu)
+#                                              + test_math_functions.py + backend / builder unit tests (≈6 min; 198 tests on b200emu)
 set -e
 REPO="$(cd "$(dirname "$0")/.." && pwd)"
 WORK="${TMPDIR:-/tmp}/gt4py_b200_reftests"; mkdir -p "$WORK/cache"; cd "$WORK"
@@ -10,6 +10,8 @@ export PYTHONPATH="$REPO/tests:$REPO/tools/shims:/root/reference/src:$REPO:/root
 export GT_CACHE_ROOT="$WORK/cache"
 I=/root/reference/tests/cartesian_tests/integration_tests
 T=$I/multi_feature_tests
-if [ $# -eq 0 ]; then set -- "$T/test_suites.py" "$T/test_math_functions.py" "$I/feature_tests"; fi
+U=/root/reference/tests/cartesian_tests/unit_tests
+if [ $# -eq 0 ]; then set -- "$T/test_suites.py" "$T/test_math_functions.py" "$I/feature_tests" \
+    "$U/backend_tests/test_backend.py" "$U/backend_tests/test_module_generator.py" "$U/test_stencil_builder.py" "$U/test_lazy_stencil.py"; fi
 python -m pytest -p emu.emu_backend_plugin -p no:cacheprovider --rootdir="$WORK" -c /dev/null -q -W ignore \
     "$T/test_code_generation.py" "$@" -k b200emu
