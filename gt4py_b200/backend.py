@@ -239,6 +239,10 @@ class B200Backend(BaseBackend):
         "seq_prefetch": {"versioning": True, "type": bool},
         "interior_loop": {"versioning": True, "type": object},  # True | "steady"
         "static_pitch": {"versioning": True, "type": int},
+        "stcs": {"versioning": True, "type": bool},  # streaming (evict-first) stores
+        "ldcs": {"versioning": True, "type": bool},  # streaming loads instead of the read-only path
+        "min_blocks": {"versioning": True, "type": int},
+        "fuse_loops": {"versioning": True, "type": bool},
         "specialize": {"versioning": True, "type": str},  # "off" | "lazy": per-pitch kernels at first call
         "verbose": {"versioning": False, "type": bool},
     }
@@ -254,7 +258,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -336,6 +336,8 @@ class StreamKernel:
 
     def emit(self) -> int:
         gen, V, U = self.gen, self.V, self.U
+        _HINTS["ld"] = "__ldcs" if self.opts.get("ldcs", False) else "__ldg"
+        _HINTS["st"] = "__stcs" if self.opts.get("stcs", False) else ""
         name = gen._kname("stream")
         A = "A"
         L: List[str] = []
@@ -801,10 +803,15 @@ def _vec_type(ct: str, V: int) -> Tuple[str, List[str]]:
     raise NotStreamable("vector size")
 
 
+#: cache hints of the vector accesses of the kernel being emitted (set by StreamKernel.emit from the
+#: options `ldcs` / `stcs`): streaming (evict-first) loads instead of the read-only path, streaming stores
+_HINTS = {"ld": "__ldg", "st": ""}
+
+
 def _vec_load(ct: str, V: int, regs: List[str], addr: str, ro: bool = True) -> str:
     """16-byte load into V scalar registers (bit casts keep any 4/8-byte element type);
     `ro`: the field is never written by this kernel -> read-only (non-coherent) path."""
-    ld = "__ldg" if ro else "*"
+    ld = _HINTS["ld"] if ro else "*"
     if ct in ("float", "int"):
         cast = "__int_as_float" if ct == "float" else ""
         comps = ["x", "y", "z", "w"][:V]
@@ -825,13 +832,16 @@ def _vec_load(ct: str, V: int, regs: List[str], addr: str, ro: bool = True) -> s
 def _vec_store(ct: str, V: int, regs: List[str], addr: str) -> str:
     if ct == "float":
         vt = "float4" if V == 4 else "float2"
-        return f"*reinterpret_cast<{vt}*>({addr}) = make_{vt}({', '.join(regs)});"
-    if ct == "int":
+    elif ct == "int":
         vt = "int4" if V == 4 else "int2"
-        return f"*reinterpret_cast<{vt}*>({addr}) = make_{vt}({', '.join(regs)});"
-    if ct == "double":
-        return f"*reinterpret_cast<double2*>({addr}) = make_double2({regs[0]}, {regs[1]});"
-    return f"*reinterpret_cast<longlong2*>({addr}) = make_longlong2({regs[0]}, {regs[1]});"
+    elif ct == "double":
+        vt = "double2"
+    else:
+        vt = "longlong2"
+    val = f"make_{vt}({', '.join(regs[: 2 if vt in ('double2', 'longlong2') else V])})"
+    if _HINTS["st"]:
+        return f"{_HINTS['st']}(reinterpret_cast<{vt}*>({addr}), {val});"
+    return f"*reinterpret_cast<{vt}*>({addr}) = {val};"
 
 
 # ---------------------------------------------------------------------------------------------------

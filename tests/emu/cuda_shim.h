@@ -34,6 +34,8 @@ inline double2 make_double2(double x, double y) { return {x, y}; }
 inline longlong2 make_longlong2(long long x, long long y) { return {x, y}; }
 
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline void __stcs(T* p, T v) { *p = v; }
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline double __hiloint2double(int hi, int lo) {
