@@ -132,3 +132,66 @@ def test_autotune_control_flow_with_a_stubbed_device(monkeypatch):
     assert len(tuned) == 3
     json_ok = __import__("json").dumps({"autotune": tuned, "options": stencil.backend_options})
     assert "static_pitch" in json_ok
+
+
+def test_stencil_graph_control_flow_with_a_stubbed_launcher(monkeypatch):
+    """StencilGraph: capture on a private stream when the current stream is the (uncapturable) legacy
+    default stream, route launches that pass no stream to it for the duration of the block, restore
+    afterwards, close the capture when the body raises."""
+    import ctypes
+
+    from gt4py_b200 import graph
+
+    log = []
+
+    class FakeLib:
+        def b200_stream_create(self, ref):
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x5000
+            return 0
+
+        def b200_graph_begin(self, s):
+            log.append(("begin", s.value))
+            return 0
+
+        def b200_graph_end(self, s, ref):
+            log.append(("end", s.value))
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x7000
+            return 0
+
+        def b200_graph_num_nodes(self, h):
+            return 3
+
+        def b200_graph_launch(self, h, s):
+            log.append(("launch", h.value, s.value or 0))
+            return 0
+
+        def b200_graph_destroy(self, h):
+            log.append(("destroy", h.value))
+            return 0
+
+        def b200_stream_destroy(self, s):
+            return 0
+
+    monkeypatch.setattr(runtime, "load_library", lambda *a, **k: FakeLib())
+    monkeypatch.setattr(runtime, "_stream_override", type("L", (), {})())
+    import torch
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: type("S", (), {"cuda_stream": 0})())
+    g = graph.StencilGraph()
+    with g:
+        assert runtime.current_stream_handle() == 0x5000 == g.stream  # launches are redirected
+    assert runtime.current_stream_handle() == 0 and log == [("begin", 0x5000), ("end", 0x5000)]
+    assert g.num_nodes == 3
+    g.launch()
+    assert log[-1] == ("launch", 0x7000, 0)
+    with pytest.raises(runtime.B200Error, match="already holds"):
+        with g:
+            pass
+    g2 = graph.StencilGraph(stream=0x9000)  # an explicit capturable stream is used as is
+    with pytest.raises(KeyError):
+        with g2:
+            assert g2.stream == 0x9000
+            raise KeyError("body failed")
+    assert runtime.current_stream_handle() == 0 and log[-1] == ("destroy", 0x7000)
+    with pytest.raises(runtime.B200Error, match="nothing captured"):
+        g2.launch()
