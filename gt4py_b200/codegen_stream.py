@@ -448,7 +448,15 @@ class StreamKernel:
             w("  const bool spitch = " + " && ".join(f"sj_{v.cname} == SJ" for v in streams) + ";")
             pitch_ok = " && spitch"
 
+        self._lag_of = {v.cname: v.lag for v in streams}
+
+        # static pitch: rows are addressed as p + (t*SJ + g0) + immediate (one shared offset, 2 registers
+        # less per stream) unless `row_pointers` asks for one running pointer per stream (fewer instructions)
+        self._useq = not self.SJ or bool(self.opts.get("row_pointers", False))
+
         def running_pointers():
+            if not self._useq:
+                return
             for v in streams:
                 ct = CT[v.dtype]
                 const = "const " if v.kind == "in" else ""
@@ -457,12 +465,14 @@ class StreamKernel:
         def steady_loop(mode, cond, bound):
             w(f"  if ({cond}) for (; t + {U} <= {bound}; t += {U}) {{   // steady loop ({mode})")
             w(f"    B200_TRACE({3 if mode == 'interior' else (0 if mode == 'pure' else 1)});")
+            if not self._useq:
+                w("    const long long toff = (long long)t * SJ + g0;   // this trip's row offset, shared by all streams")
             for u in range(U):
                 w(f"    {{  // steady step, rotation phase {(ph0 + u) % U}")
                 w(f"      const int tt = t + {u};")
                 L.extend(self._emit_step((ph0 + u) % U, fast=mode, u=u))
                 w("    }")
-            if self.SJ:
+            if self.SJ and self._useq:
                 for v in streams:
                     w(f"    q_{v.cname} += {U} * SJ;")
             w("  }")
@@ -633,6 +643,9 @@ class StreamKernel:
 
     def _row_addr(self, c: str, ahead: int = 0) -> str:
         """Address of this lane's vector in the row the current steady step touches (+ `ahead` rows)."""
+        if self.SJ and not self._useq:
+            k = self._u + ahead - self._lag_of[c]
+            return f"(p_{c} + toff + ({k}) * SJ)"
         if self.SJ:
             k = self._u + ahead
             return f"(q_{c} + {k} * SJ)" if k else f"q_{c}"

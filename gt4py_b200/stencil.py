@@ -323,6 +323,9 @@ class B200Stencil:
         {"interior_loop": True, "static_pitch": "auto", "vector_width": 4},
         {"interior_loop": True, "static_pitch": "auto", "vector_width": 4, "prefetch": 0},
         {"interior_loop": "steady", "static_pitch": "auto"},
+        {"interior_loop": True, "static_pitch": "auto", "row_pointers": True},
+        {"interior_loop": "steady", "static_pitch": "auto", "row_pointers": True},
+        {"static_pitch": "auto", "row_pointers": True},
         {"interior_loop": True, "static_pitch": "auto", "stcs": True},
         {"interior_loop": True, "static_pitch": "auto", "stcs": True, "ldcs": True},
         {"interior_loop": True, "static_pitch": "auto", "tile_j": 52},

@@ -107,6 +107,7 @@ def test_subbox_launches_compose(name, variant, strategy):
         {"interior_loop": True, "static_pitch": 160, "vector_width": 4, "prefetch": 0},
         {"interior_loop": True, "static_pitch": 160, "l2_prefetch": 0, "tile_j": 32, "warps": 2},
         {"interior_loop": True, "static_pitch": 160, "stcs": True, "ldcs": True}, {"stcs": True},
+        {"interior_loop": True, "static_pitch": 160, "row_pointers": True}, {"static_pitch": 160, "row_pointers": True},
         {"interior_loop": "steady", "static_pitch": 160}, {"interior_loop": True, "static_pitch": 160, "tile_j": 52, "min_blocks": 8},
         {"interior_loop": True, "static_pitch": 192},  # pitch of the arguments differs -> general loop, same result
     ],
