@@ -24,8 +24,9 @@ Parity pin: `tests/golden/*.npz` hold outputs of the *reference itself* (its `nu
 imported from /root/reference in the build container by `tools/make_golden.py`); the CPU test-suite
 checks this interpreter against every one of them bit for bit.
 
-Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu-baseline / `--impl reference` legs may
-import this module.
+Only `tests/`, `__graft_entry__.smoke()`, the cpu-baseline / `--impl reference` legs of `bench.py`
+(and of its sibling for the other configs, `tools/bench_workloads.py`) and the golden-vector generator
+`tools/make_golden.py` may import this module; nothing under `gt4py_b200/` does.
 """
 
 from __future__ import annotations
