@@ -243,6 +243,7 @@ class B200Backend(BaseBackend):
         "ldcs": {"versioning": True, "type": bool},  # streaming loads instead of the read-only path
         "min_blocks": {"versioning": True, "type": int},
         "row_pointers": {"versioning": True, "type": bool},
+        "fuse_columns": {"versioning": True, "type": bool},
         "fuse_loops": {"versioning": True, "type": bool},
         "specialize": {"versioning": True, "type": str},  # "off" | "lazy": per-pitch kernels at first call
         "verbose": {"versioning": False, "type": bool},
@@ -259,7 +260,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -444,9 +444,36 @@ class Generator:
             secs.append({"interval": sec["interval"], "kernels": ks})
         self.steps.append({"t": "levels", "order": order, "sections": secs})
 
-    def generate(self) -> Tuple[str, Dict[str, Any]]:
-        for loop in self.st["loops"]:
+    def lower_loops(self, loops: List[dict]) -> None:
+        """Lower a run of consecutive loops; consecutive FORWARD/BACKWARD sweeps whose data flow stays
+        inside a column become ONE column kernel (forward elimination + back substitution of a
+        tridiagonal solve in one launch) when `fuse_columns` is on.  Off by default: the fused kernel
+        runs every sweep at the register count of the heaviest one (Thomas: the 32-register back
+        substitution would run at the 58 registers of the elimination, 36 instead of 64 warps/SM), which
+        can cost more than the saved launch and the L2 hits on the freshest levels — to be measured."""
+        from . import codegen_column
+
+        n = 0
+        while n < len(loops):
+            loop = loops[n]
+            group = [loop]
+            if loop["order"] != "parallel" and not _needs_level_sync(loop) and self.opt.get("fuse_columns", False):
+                m = n + 1
+                while (m < len(loops) and loops[m]["order"] != "parallel" and not _needs_level_sync(loops[m])
+                       and all(codegen_column.fusable(g, loops[m]) for g in group)):  # fmt: skip
+                    group.append(loops[m])
+                    m += 1
+            if len(group) > 1:
+                k = codegen_column.try_emit(self, group, self.opt)
+                if k is not None:
+                    self.steps.append({"t": "launch", "kernel": k})
+                    n += len(group)
+                    continue
             self.lower_loop(loop)
+            n += 1
+
+    def generate(self) -> Tuple[str, Dict[str, Any]]:
+        self.lower_loops(self.st["loops"])
         return self.finish()
 
     def finish(self) -> Tuple[str, Dict[str, Any]]:

@@ -50,16 +50,16 @@ def _tag(key: Key) -> str:
 
 
 class ColumnKernel:
-    def __init__(self, gen, loop: dict, opts: Dict[str, Any]):
+    def __init__(self, gen, loops: List[dict], opts: Dict[str, Any]):
         from . import codegen as cg
 
         self.cg = cg
         self.gen = gen
         self.ft = gen.ft
-        self.loop = loop
+        self.loops = loops  # consecutive sweeps executed back to back by the same thread (see fusable())
         self.opts = opts
-        self.step = 1 if loop["order"] == "forward" else -1
-        self.hes = [he for sec in loop["sections"] for he in sec["hes"]]
+        self.step = 1
+        self.hes = [he for loop in loops for sec in loop["sections"] for he in sec["hes"]]
         if not self.hes:
             raise NotColumnable("empty loop")
         ext = self.hes[0]["extent"]
@@ -68,6 +68,7 @@ class ColumnKernel:
         self.extent = ext
         acc = [a for he in self.hes for a in b2ir.field_accesses(he["body"])]
         self.written: Set[str] = {a["name"] for a in acc if a["write"]}
+        self.loop_written: Set[str] = set(self.written)  # fields written by the sweep being emitted
         for a in acc:
             if a["write"] and (isinstance(a["off"], dict) or tuple(a["off"]) != (0, 0, 0)):
                 raise NotColumnable("write at an offset")
@@ -253,7 +254,7 @@ class ColumnKernel:
                     continue
                 name, di, dj, dk = key
                 # the cell loaded `depth` levels early must not be written by the levels in between
-                if name in self.written and -self.depth <= dk * step < 0:
+                if name in self.loop_written and -self.depth <= dk * step < 0:
                     continue
                 prefetched.append(key)
         return carried, prefetched
@@ -274,14 +275,16 @@ class ColumnKernel:
             ct = CT[self.ft.entries[n]["dtype"]]
             const = "" if fname in self.written else "const "
             w(f"  {const}{ct}* const c_{cg._cname(fname)} = ({const}{ct}*)A.f[{n}].p + (long long)i * A.f[{n}].s[0] + (long long)j * A.f[{n}].s[1];")
-        fwd = self.step == 1
-        for si, sec in enumerate(self.loop["sections"]):
+        for li, si, loop, sec in [(li, si, lp, sec) for li, lp in enumerate(self.loops) for si, sec in enumerate(lp["sections"])]:
+            self.step = 1 if loop["order"] == "forward" else -1
+            fwd = self.step == 1
+            self.loop_written = {a["name"] for sc in loop["sections"] for he in sc["hes"] for a in b2ir.field_accesses(he["body"]) if a["write"]}
             carried, prefetched = self._plan_section(sec)
             live = set(carried) | set(prefetched)
             body, exposed, final, touched = self._emit_level(sec, live)
             k0 = cg._bound(sec["interval"][0], "A.g.nK")
             k1 = cg._bound(sec["interval"][1], "A.g.nK")
-            w(f"  {{  // section {si}: carried {[_tag(c) for c in carried]}, prefetched {[_tag(p) for p in prefetched]}")
+            w(f"  {{  // {loop['order']} sweep {li}, section {si}: carried {[_tag(c) for c in carried]}, prefetched {[_tag(p) for p in prefetched]}")
             w(f"    const int k0 = {k0}, k1 = {k1};")
             w("    if (k0 < k1) {")
             for key in sorted(touched | live):
@@ -327,12 +330,30 @@ class ColumnKernel:
         return len(gen.kernels) - 1
 
 
-def try_emit(gen, loop: dict, opts: Dict[str, Any]) -> Optional[int]:
-    """Emit `loop` (FORWARD/BACKWARD, no level synchronisation needed) as one column kernel with
-    register k-caches; returns the kernel index or None when the template does not apply."""
+def fusable(a: dict, b: dict) -> bool:
+    """Sweep `b` may follow sweep `a` inside the same thread (one launch, the column's freshest levels
+    still in L1/L2 when `b` starts) when no value crosses columns between them: neither reads at an IJ
+    offset a field the other one writes."""
+
+    def rw(loop):
+        acc = [x for sec in loop["sections"] for he in sec["hes"] for x in b2ir.field_accesses(he["body"])]
+        written = {x["name"] for x in acc if x["write"]}
+        off = {x["name"] for x in acc if not x["write"] and b2ir.ij_offset(x["off"]) != (0, 0)}
+        return written, off
+
+    wa, oa = rw(a)
+    wb, ob = rw(b)
+    return not (wa & ob) and not (wb & oa)
+
+
+def try_emit(gen, loops, opts: Dict[str, Any]) -> Optional[int]:
+    """Emit one or several consecutive FORWARD/BACKWARD loops (no level synchronisation needed) as ONE
+    column kernel with register k-caches; returns the kernel index or None when the template does not apply."""
     if not opts.get("seq_cache", True):
         return None
+    if isinstance(loops, dict):
+        loops = [loops]
     try:
-        return ColumnKernel(gen, loop, opts).emit()
+        return ColumnKernel(gen, list(loops), opts).emit()
     except NotColumnable:
         return None

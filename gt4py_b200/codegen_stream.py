@@ -991,10 +991,13 @@ def _generate(stencil: Dict[str, Any], options: Dict[str, Any], *, strict: bool)
         if all(_defined_before_use(stencil["loops"][li]["sections"][si]["hes"], t) for (li, si) in secs if t in touched[(li, si)])
         and all(stencil["loops"][li]["order"] == "parallel" for (li, si) in secs if t in touched[(li, si)])
     }  # fmt: skip
+    pending: List[dict] = []  # run of consecutive sequential loops (may fuse into one column kernel)
     for li, loop in enumerate(stencil["loops"]):
         if loop["order"] != "parallel":
-            gen.lower_loop(loop)
+            pending.append(loop)
             continue
+        gen.lower_loops(pending)
+        pending = []
         plans = []
         ok = True
         for si, sec in enumerate(loop["sections"]):
@@ -1016,6 +1019,7 @@ def _generate(stencil: Dict[str, Any], options: Dict[str, Any], *, strict: bool)
             k = sk.emit()
             gen.steps.append({"t": "launch", "kernel": k})
             used_stream = True
+    gen.lower_loops(pending)
     if not used_stream:
         return None
     return gen.finish()

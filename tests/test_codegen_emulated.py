@@ -123,7 +123,8 @@ SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lo
 
 
 @pytest.mark.parametrize("name", SEQ_CASES)
-@pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"seq_cache": False}])
+@pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"seq_cache": False},
+                                  {"fuse_columns": True}, {"fuse_columns": True, "seq_prefetch": 2}])  # fmt: skip
 def test_column_generator_variants(name, opts):
     """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
     baseline column kernel: same results on ragged domains, both lowerings"""
@@ -138,8 +139,10 @@ def test_column_generator_keeps_the_k_dataflow_in_registers():
     k-1 values of sup / rhs carried in registers (no load)."""
     from gt4py_b200 import codegen
 
-    src, plan = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {})
-    sweep = src[src.index("section 1"):src.index("b200_tridiagonal_f64_col1")]
+    src, plan = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {"fuse_columns": True})
+    assert [k["name"] for k in plan["kernels"]] == ["b200_tridiagonal_f64_col0"]  # both sweeps, one launch
+    sweep = src[src.index("forward sweep 0, section 1"):src.index("backward sweep 1, section 0")]
+    assert len(codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {})[1]["kernels"]) == 2  # default: one per sweep
     loop = sweep[sweep.index("for (int k"):]
     assert "carried ['sup_p0p0m1', 'rhs_p0p0m1']" in sweep
     assert loop.count("b200::ldro<double>") == 2 and loop.count("= c_sup[") == 1 and loop.count("= c_rhs[") == 1

@@ -40,6 +40,7 @@ def test_column_solvers_domains(name, domain):
     run_case(name, "default", None, domain=domain, seed=4)
     run_case(name, "staged", {"seq_prefetch": False}, domain=domain, seed=5)
     run_case(name, "default", {"seq_cache": False}, domain=domain, seed=6)
+    run_case(name, "default", {"fuse_columns": True, "seq_prefetch": 2}, domain=domain, seed=7)
 
 
 def test_c_order_torch_tensors_any_stride():

@@ -36,7 +36,8 @@ def main():
         {"interior_loop": True, "static_pitch": PITCH, "vector_width": 4, "prefetch": 0},
         {"interior_loop": True, "static_pitch": PITCH, "l2_prefetch": 4},
     ]  # fmt: skip
-    col_variants = [{"seq_cache": False}, {"seq_prefetch": 0}, {}, {"seq_prefetch": 2}, {"seq_prefetch": 3}]
+    col_variants = [{"seq_cache": False}, {"seq_prefetch": 0}, {}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"fuse_columns": True},
+                    {"fuse_columns": True, "seq_prefetch": 2}]  # fmt: skip
     runs = []
     for v in stream_variants:
         runs.append(("hdiff_f32", "staged", (1024 // q, 1024 // q, 80), v))  # config 2
