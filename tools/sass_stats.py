@@ -46,7 +46,7 @@ TABLE = [
     ("hdiff_f32", {}), ("hdiff_f32", {"static_pitch": 1056}), ("hdiff_f32", {"interior_loop": True}),
     ("hdiff_f32", {"interior_loop": "steady", "static_pitch": 1056}),
     ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056}),
-    ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056, "min_blocks": 8}),
+    ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056, "row_pointers": True}),
     ("hdiff_f32", {"interior_loop": True, "static_pitch": 1056, "vector_width": 4}),
     ("upwind5_f32", {}), ("upwind5_f32", {"interior_loop": True, "static_pitch": 2080}),
     ("tridiagonal_f64", {"seq_cache": False}), ("tridiagonal_f64", {}),
