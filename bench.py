@@ -44,7 +44,7 @@ STENCIL, VARIANT = "hdiff_f32", "staged"
 BYTES_PER_CELL = 12
 METRIC = "Mcell-updates/s + achieved HBM GB/s, horiz-diffusion 1024x1024x80 fp32"
 CPU_SAMPLE = (256, 256, 16)
-STRIP = 64  # rows of the boundary strips in the overlapped multi-GPU step (= J tile of the streaming kernel)
+STRIP = 64  # rows of the boundary strips in the overlapped multi-GPU step (reset to the tuned J tile of the kernel)
 
 
 def measured_peaks():
@@ -180,8 +180,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--strategy", default="auto")
-    ap.add_argument("--overlap", action="store_true", help="overlap the halo exchange with the interior tiles (N>1)")
-    ap.add_argument("--no-overlap", action="store_true", help="(default) exchange, then compute the whole slab")
+    ap.add_argument("--overlap", action="store_true", help="N>1: always overlap the halo exchange with the interior tiles")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: always exchange first, then compute the whole slab")
     ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the default code-generation options")
@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--pipeline-chunks", type=int, default=10, help="K slabs of the host pipeline (e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # N>1 default: time a few steps of both orders after the warm-up and keep the faster one (decided on
+    # the max over ranks, so every rank takes the same decision)
+    args.overlap_mode = "on" if args.overlap else ("off" if args.no_overlap else "auto")
     args.no_overlap = not args.overlap
 
     # never hang the box: a lost peer / unmatched exchange turns into a loud non-zero exit
@@ -260,6 +263,10 @@ def run_b200(args):
         except Exception as exc:  # keep the measured default rather than lose the bench line
             tuned = f"autotune failed, default options used: {type(exc).__name__}: {exc}"
     frozen = stencil.freeze(origin=origins, domain=domain)
+    global STRIP
+    STRIP = int(stencil.backend_options.get("tile_j", 64))  # boundary strips = whole J tiles of the tuned kernel
+    if 2 * STRIP >= NJ:
+        STRIP = 64
 
     exchanger = None
     if world > 1:
@@ -315,6 +322,25 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     barrier()
+    overlap_trial = None
+    if exchanger is not None and args.overlap_mode == "auto":
+        trial = {}
+        for mode in ("off", "on"):
+            args.no_overlap = mode == "off"
+            for i in range(2):
+                step(i)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(6):
+                step(i)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / 6], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            trial[mode] = round(float(t.item()), 5)
+        args.no_overlap = trial["off"] <= trial["on"]
+        overlap_trial = {"ms_per_step_no_overlap": trial["off"], "ms_per_step_overlap": trial["on"]}
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
     # (clock sampling on rank 0 only: one nvidia-smi query stream for the whole job)
@@ -465,7 +491,8 @@ def run_b200(args):
                 "workload": f"horizontal diffusion (lap-of-lap + flux limiter) {NI}x{NJ}x{NK} fp32 per GPU "
                 f"(BASELINE configs[1]), literal_float_precision=32, fields {shape} origin {origin3}",
                 "parallelism": "single GPU" if n_gpus == 1 else f"J-slab decomposition x{n_gpus}, NCCL halo exchange "
-                + ("(no overlap)" if args.no_overlap else "overlapped with interior"),
+                + ("(no overlap)" if args.no_overlap else "overlapped with interior")
+                + (f"; order chosen by trial {overlap_trial}" if overlap_trial else ""),
                 "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
                 "strategy": args.strategy,
                 "codegen_options": stencil.backend_options,

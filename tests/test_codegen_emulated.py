@@ -95,6 +95,10 @@ def test_subbox_launches_compose(name, variant, strategy):
     boxes = [(0, 37, 0, nj), (37, 61, 0, 3), (37, 61, 3, nj), (61, ni, 0, nj)]
     run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=4, subboxes=boxes)
     run_emulated(name, variant, {"strategy": strategy}, domain=(ni, nj, 2), seed=4, subboxes=boxes, layout="b200", guard="end")
+    if strategy == "auto":  # the tuned variants bench.py may pick, launched strip by strip (multi-GPU overlap)
+        tuned = {"interior_loop": True, "static_pitch": 96, "tile_j": 32}
+        boxes = [(0, ni, 32, nj - 32), (0, ni, 0, 32), (0, ni, nj - 32, nj)]
+        run_emulated(name, variant, tuned, domain=(ni, nj, 2), seed=5, subboxes=boxes, layout="b200", guard="end")
 
 
 @pytest.mark.parametrize(
