@@ -170,3 +170,33 @@ def test_loop_fusion_by_interval_refinement(name):
     for opts in ({}, {"fuse_loops": False}, {"interior_loop": True, "static_pitch": 160}):
         run_emulated(name, "staged", opts, domain=(139, 70, 4), seed=13, layout="b200", guard="end")
         run_emulated(name, "default", opts, domain=(21, 9, 3), seed=14)
+
+
+def test_loop_fusion_legality_rules():
+    """_can_fuse on hand-made loops: K-offset read of the producer's output, an offset read of a field
+    the later loop overwrites, and interval bounds whose order depends on the domain size are refused"""
+    from gt4py_b200 import codegen_stream as cs
+
+    def fld(name, off=(0, 0, 0)):
+        return {"t": "field", "name": name, "dtype": "float64", "off": list(off), "data_index": []}
+
+    def loop(assigns, interval=(("start", 0), ("end", 0))):
+        body = [{"t": "assign", "left": fld(left), "right": right} for left, right in assigns]
+        return {"order": "parallel", "caches": [], "sections": [{"interval": [list(interval[0]), list(interval[1])],
+                "hes": [{"locals": [], "extent": [[0, 0], [0, 0]], "body": body}]}]}  # fmt: skip
+
+    st = {"domain_info": {"min_k": 2}}
+    a = loop([("t", fld("x"))])
+    assert cs._can_fuse(a, loop([("y", fld("t", (1, 0, 0)))]), st)  # IJ-offset hand-over: register windows
+    assert not cs._can_fuse(a, loop([("y", fld("t", (0, 0, 1)))]), st)  # level k+1 of t may not exist yet
+    assert not cs._can_fuse(loop([("t", fld("x", (0, 1, 0)))]), loop([("x", fld("t"))]), st)  # WAR on x
+    assert cs._can_fuse(loop([("t", fld("x"))]), loop([("x", fld("t"))]), st)  # zero-offset read-modify-write is fine
+    lo = loop([("t", fld("x"))], (("start", 0), ("start", 4)))
+    hi = loop([("y", fld("t"))], (("end", -1), ("end", 0)))
+    assert not cs._can_fuse(lo, hi, st)  # start+4 <= end-1 needs nK >= 5 > min_k
+    assert cs._can_fuse(lo, hi, {"domain_info": {"min_k": 5}})
+    fused = cs._fuse(lo, hi)
+    assert [s["interval"] for s in fused["sections"]] == [[["start", 0], ["start", 4]], [["end", -1], ["end", 0]]]
+    both = cs._fuse(loop([("t", fld("x"))]), loop([("y", fld("t"))], (("start", 1), ("end", -1))))
+    assert [(s["interval"], len(s["hes"])) for s in both["sections"]] == [
+        ([["start", 0], ["start", 1]], 1), ([["start", 1], ["end", -1]], 2), ([["end", -1], ["end", 0]], 1)]  # fmt: skip
