@@ -228,8 +228,11 @@ class B200Backend(BaseBackend):
         "oir_pipeline": {"versioning": True, "type": passes.OirPipeline},
         "strategy": {"versioning": True, "type": str},  # "auto" | "point"
         "fmad": {"versioning": True, "type": bool},
-        "opt_level": {"versioning": True, "type": int},
+        "opt_level": {"versioning": True, "type": str},  # "0".."3" like gt:gpu (ints accepted too)
+        "extra_opt_flags": {"versioning": True, "type": str},  # extra nvcc flags, space separated
         "debug_mode": {"versioning": True, "type": bool},
+        "add_profile_info": {"versioning": True, "type": bool},  # accepted for gt:gpu compatibility (-lineinfo is always on)
+        "clean": {"versioning": False, "type": bool},  # accepted for gt:gpu compatibility (nothing to clean: no build tree)
         "tile_j": {"versioning": True, "type": int},
         "warps": {"versioning": True, "type": int},
         "vector_width": {"versioning": True, "type": int},
@@ -259,7 +262,7 @@ class B200Backend(BaseBackend):
         return f"{caching.module_prefix}b200_ir{caching.module_postfix}.json"
 
     def codegen_options(self) -> Dict[str, Any]:
-        keep = ("strategy", "fmad", "opt_level", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
+        keep = ("strategy", "fmad", "opt_level", "extra_opt_flags", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
                 "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 

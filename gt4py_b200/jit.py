@@ -40,11 +40,13 @@ def nvcc_path() -> str:
 
 def compile_flags(options: Optional[Dict] = None) -> list:
     options = options or {}
-    flags = list(ARCH_FLAGS) + ["-std=c++17", "-lineinfo", f"-O{int(options.get('opt_level', 3))}"]
+    opt = str(options.get("opt_level", 3))  # the reference passes "0".."3" / "s" as strings (gtc_common.py:192)
+    flags = list(ARCH_FLAGS) + ["-std=c++17", "-lineinfo", f"-O{int(opt) if opt.isdigit() else 3}"]
     flags.append("-fmad=true" if options.get("fmad", False) else "-fmad=false")
     if options.get("debug_mode", False):
         flags += ["-G"]
-    flags += list(options.get("extra_opt_flags", []) or [])
+    extra = options.get("extra_opt_flags", []) or []
+    flags += extra.split() if isinstance(extra, str) else list(extra)  # reference: one space-separated string
     return flags
 
 

@@ -92,7 +92,10 @@ class Gen:
                 body_t = list(temps)
                 for t in new_t:  # temporaries must be defined in every interval piece of their computation
                     L.append(f"            {t} = {self.expr(inputs, body_t, r.randint(1, 3), koff=split is None, reach=2)}")
-                    # (not readable at an offset inside the computation that defines it unless staged; keep to later ones)
+                    if r.random() < 0.3:  # masked redefinition
+                        L.append(f"            if {self.leaf(inputs, body_t, koff=False, reach=0)} > {self.lit()}:")
+                        L.append(f"                {t} = {self.expr(inputs, body_t, 2, koff=False, reach=1)}")
+                    body_t.append(t)  # later statements of the same computation may read it at IJ offsets (stages)
                 if ci == n_comp - 1:
                     if r.random() < 0.4 and temps:
                         cond = f"{self.leaf(inputs, temps, koff=False, reach=0)} > {self.lit()}"
@@ -104,7 +107,7 @@ class Gen:
                             L.append(f"                {o} = {self.expr(inputs, temps, 2, koff=False, reach=1)}")
                     else:
                         for o in outs:
-                            L.append(f"            {o} = {self.expr(inputs, temps, r.randint(1, 3), koff=split is None, reach=2)}")
+                            L.append(f"            {o} = {self.expr(inputs, body_t, r.randint(1, 3), koff=split is None, reach=2)}")
             temps += new_t
         return "\n".join(L) + "\n"
 
