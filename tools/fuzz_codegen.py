@@ -31,7 +31,7 @@ for p in (ROOT, ROOT / "tests"):
         sys.path.insert(0, str(p))
 
 HEADER = """import numpy as np
-from gt4py.cartesian.gtscript import PARALLEL, FORWARD, BACKWARD, Field, computation, interval, I, J, K
+from gt4py.cartesian.gtscript import PARALLEL, FORWARD, BACKWARD, Field, computation, interval, horizontal, region, I, J, K
 F = Field[np.{dtype}]
 """
 
@@ -108,6 +108,10 @@ class Gen:
                     else:
                         for o in outs:
                             L.append(f"            {o} = {self.expr(inputs, body_t, r.randint(1, 3), koff=split is None, reach=2)}")
+                    if r.random() < 0.3:  # horizontal region on an output (positional mask, may reach outside the domain)
+                        reg = r.choice(["I[0], :", ":, J[-1]", "I[0] : I[0] + 2, J[0] + 1 :", "I[-1] - 1 :, :", ":, J[0] - 1 : J[0] + 1"])
+                        L.append(f"            with horizontal(region[{reg}]):")
+                        L.append(f"                {outs[0]} = {self.expr(inputs, body_t, 2, koff=False, reach=1)}")
             temps += new_t
         return "\n".join(L) + "\n"
 
@@ -165,10 +169,13 @@ def run_case(source: str, fname: str, dtype: str, seed: int, workdir: pathlib.Pa
     ref_stencil = gtscript.stencil(backend="numpy", definition=getattr(mod, fname), name=fname + "_ref", **build_opts)
     st0 = irs["default"]
     fields, params, origins, domain = testing.make_case_data(st0, fname, domain=(17, 6, max(4, int(st0["domain_info"]["min_k"]))), seed=seed)
-    a = {k: v.copy() for k, v in fields.items()}
-    b = {k: v.copy() for k, v in fields.items()}
+    a = {k: v.copy() for k, v in fields.items() if v is not None}
+    b = {k: v.copy() for k, v in fields.items() if v is not None}
+    import inspect
+
+    unused = {n: None for n in inspect.signature(getattr(mod, fname)).parameters if n not in a}  # pruned arguments
     try:
-        ref_stencil(**a, **params, origin=origins, domain=domain)
+        ref_stencil(**a, **unused, **params, origin=origins, domain=domain)
     except Exception as exc:  # e.g. the reference's numpy code generator mis-shapes literal-only masks
         return f"SKIP reference numpy backend failed: {type(exc).__name__}: {str(exc)[:100]}"
     numpy_oracle.run(st0, b, params, domain, origins)
