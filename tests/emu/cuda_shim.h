@@ -20,12 +20,14 @@ struct emu_uint3 { unsigned x, y, z; };
 extern thread_local emu_uint3 threadIdx, blockIdx;
 extern emu_uint3 blockDim, gridDim;
 
-struct int2 { int x, y; };
-struct int4 { int x, y, z, w; };
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
-struct double2 { double x, y; };
-struct longlong2 { long long x, y; };
+// same alignment as the CUDA built-in vector types: the kernels are compiled with -fsanitize=alignment
+// (tests/emu/emu.py), so a vector load/store the device would trap on (misaligned address) aborts here too
+struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(16) longlong2 { long long x, y; };
 inline int2 make_int2(int x, int y) { return {x, y}; }
 inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 inline float2 make_float2(float x, float y) { return {x, y}; }

@@ -62,6 +62,7 @@ class EmuStencil:
             # the lockstep runtime (heavy <thread>/<barrier> headers) is compiled once; kernels at -O0:
             # compile time dominates these tests, the domains are tiny
             cmd = ["g++", "-std=c++20", "-O0", "-pthread", "-shared", "-fPIC", "-DB200_HOST_EMU", "-ffp-contract=off",
+                   "-fsanitize=alignment", "-fno-sanitize-recover=alignment",  # misaligned vector access = device trap
                    "-I", str(HERE), "-I", str(CSRC), "-x", "c++", str(src), "-x", "none", str(_runtime_object()), "-o", str(so) + ".tmp"]
             proc = subprocess.run(cmd, capture_output=True, text=True)
             if proc.returncode != 0:
