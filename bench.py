@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the default code-generation options")
+    ap.add_argument("--tune-in-process", action="store_true", help="run the autotune sweep in this process instead of a child")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: serial copy-in / call / copy-out only")
     ap.add_argument("--pipeline-chunks", type=int, default=10, help="K slabs of the host pipeline (e2e)")
     args = ap.parse_args()
@@ -258,10 +259,15 @@ def run_b200(args):
     if not args.no_autotune:
         # pick the fastest code-generation variant for this stencil x domain on this device (every
         # candidate is checked bit-for-bit against the default variant before it is timed)
+        # The sweep runs in a sacrificial child process (gt4py_b200/tune_worker.py): a variant that faults
+        # or hangs on the device cannot take this process' CUDA context, and with it the bench line.
         try:
-            tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
+            if args.tune_in_process:
+                tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
+            else:
+                tuned = stencil.autotune_isolated(sets[0], {}, domain=domain, origin=origins, timeout=min(240.0, args.watchdog / 2), device=local_rank)
         except Exception as exc:  # keep the measured default rather than lose the bench line
-            tuned = f"autotune failed, default options used: {type(exc).__name__}: {exc}"
+            tuned = f"autotune failed, default options used: {type(exc).__name__}: {str(exc)[-400:]}"
     frozen = stencil.freeze(origin=origins, domain=domain)
     global STRIP
     STRIP = int(stencil.backend_options.get("tile_j", 64))  # boundary strips = whole J tiles of the tuned kernel

@@ -358,7 +358,7 @@ class B200Stencil:
             cand["static_pitch"] = int(pitches.pop())
         return cand
 
-    def autotune(self, fields, params, *, domain, origin, candidates=None, iters: int = 10, verbose: bool = False):
+    def autotune(self, fields, params, *, domain, origin, candidates=None, iters: int = 10, verbose: bool = False, refine: int = 3):
         """Time the code-generation variants in `candidates` (option dicts merged over the current
         options) on the given device arguments and keep the fastest one whose written fields are
         bit-identical to the first candidate's (the current options).  Outputs are overwritten.
@@ -417,10 +417,96 @@ class B200Stencil:
         if not results:
             raise RuntimeError("autotune: no candidate could be built")
         results.sort(key=lambda r: r[1])
+        # the sweep's 10-launch timings are a few per cent noisy: re-time the leaders (interleaved, best of
+        # `refine` rounds) so that the choice among near-equal variants is not a coin toss
+        if refine and len(results) > 1:
+            top = results[: min(6, len(results))]
+            best_ms = {id(r[2]): r[1] for r in top}
+            for _ in range(int(refine)):
+                for cand, _ms, cs, _opts in top:
+                    scal, descs = cs.pack_scalars(params), cs.make_field_descs(views, origin)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _i in range(2 * iters):
+                        cs.run_descs(descs, scal, domain)
+                    e1.record()
+                    e1.synchronize()
+                    best_ms[id(cs)] = min(best_ms[id(cs)], e0.elapsed_time(e1) / (2 * iters))
+            results = sorted([(r[0], best_ms[id(r[2])], r[2], r[3]) for r in top], key=lambda r: r[1]) + results[len(top):]
         best = results[0]
         self.compiled, self.backend_options = best[2], best[3]
         self.tuned = [(r[0], round(r[1], 5)) for r in results]
         self.tune_rejected = rejected
+        return self.tuned
+
+    def autotune_isolated(self, fields, params, *, domain, origin, candidates=None, iters: int = 10, timeout: float = 300.0,
+                          device: Optional[int] = None):  # fmt: skip
+        """`autotune` with the candidate sweep in a sacrificial child process (gt4py_b200/tune_worker.py) on
+        synthetic arguments of the same geometry: a variant that faults or hangs on the device cannot take
+        the caller's CUDA context with it.  The parent then walks the child's ranking and adopts the first
+        variant that is bit-identical to the current one on the REAL arguments (outputs are overwritten).
+        Raises if the child fails; the current options stay in force in that case."""
+        import json
+        import os
+        import subprocess
+        import tempfile
+
+        import torch
+
+        views = {n: (runtime.as_view(fields[n]) if fields.get(n) is not None else None) for n in self._field_names}
+        spec = {
+            "name": self.name, "ir": self.ir, "options": self.backend_options, "params": {k: (v.item() if hasattr(v, "item") else v) for k, v in params.items()},
+            "domain": [int(d) for d in domain], "origin": {k: [int(x) for x in v] for k, v in origin.items()},
+            "candidates": [dict(c) for c in (candidates if candidates is not None else self.DEFAULT_CANDIDATES)],
+            "iters": int(iters), "device": int(torch.cuda.current_device() if device is None else device),
+            "fields": {n: (None if v is None else {"shape": list(v.shape), "strides": list(v.strides), "dtype": v.dtype.name, "phase": v.ptr % 256})
+                       for n, v in views.items()},
+        }  # fmt: skip
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+            json.dump(spec, fh)
+            spec_path = fh.name
+        try:
+            env = dict(os.environ)
+            root = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+            env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+                env.pop(k, None)  # the child is a plain single-device process
+            proc = subprocess.run([sys.executable, "-m", "gt4py_b200.tune_worker", spec_path], capture_output=True, text=True,
+                                  timeout=timeout, env=env)  # fmt: skip
+        finally:
+            try:
+                os.unlink(spec_path)
+            except OSError:
+                pass
+        if proc.returncode != 0:
+            raise RuntimeError(f"autotune worker exited with {proc.returncode}: {proc.stderr[-600:]}")
+        res = json.loads(proc.stdout.strip().splitlines()[-1])
+        ranking = [(c, float(ms)) for c, ms in res["tuned"]]
+        self.tune_rejected = list(res.get("rejected", []))
+        written = [n for n, fi in self.field_info.items() if fi is not None and fi.access in ("WRITE", "READ_WRITE") and views.get(n) is not None]
+
+        def outputs():
+            ts = [fields[n].torch() if isinstance(fields[n], b2storage.DeviceArray) else fields[n] for n in written]
+            return [t for t in ts if hasattr(t, "clone") and hasattr(t, "zero_")]
+
+        def run_and_snapshot(cs):
+            for t in outputs():
+                t.zero_()
+            cs.run_descs(cs.make_field_descs(views, origin), cs.pack_scalars(params), domain)
+            torch.cuda.synchronize()
+            return [t.clone() for t in outputs()]
+
+        expect = run_and_snapshot(self.compiled)
+        base = dict(self.backend_options)
+        for cand, _ms in ranking:
+            opts = {**base, **cand}
+            cs = runtime.CompiledStencil(self.ir, opts, name=self.name)  # cubin: disk cache written by the child
+            got = run_and_snapshot(cs)
+            if all(torch.equal(a, b) for a, b in zip(expect, got)):
+                self.compiled, self.backend_options = cs, opts
+                break
+            self.tune_rejected.append({"rejected_on_real_arguments": cand})
+        self.tuned = [(c, round(ms, 5)) for c, ms in ranking]
         return self.tuned
 
     def freeze(self, *, origin: Dict[str, Tuple[int, ...]], domain: Tuple[int, ...]) -> "FrozenStencil":

@@ -37,7 +37,7 @@ class _FakeStream:
         pass
 
 
-@pytest.mark.parametrize("extra", [[], ["--no-autotune", "--no-pipeline"]])
+@pytest.mark.parametrize("extra", [[], ["--tune-in-process"], ["--no-autotune", "--no-pipeline"]])
 def test_bench_main_dry_run(monkeypatch, capsys, extra):
     import torch
 
@@ -64,6 +64,27 @@ def test_bench_main_dry_run(monkeypatch, capsys, extra):
         return len(self.plan["kernels"])
 
     monkeypatch.setattr(runtime.CompiledStencil, "run_descs", fake_run)
+
+    # the autotune child (`python -m gt4py_b200.tune_worker spec.json`) runs in-process under the same stubs
+    import io
+    import subprocess
+
+    real_run = subprocess.run
+    worker_calls = []
+
+    def fake_subprocess_run(cmd, *a, **kw):
+        if "gt4py_b200.tune_worker" not in cmd:
+            return real_run(cmd, *a, **kw)
+        from gt4py_b200 import tune_worker
+
+        assert kw.get("timeout") and "RANK" not in kw["env"]
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            rc = tune_worker.main([cmd[-1]])
+        worker_calls.append(cmd)
+        return subprocess.CompletedProcess(cmd, rc, stdout=buf.getvalue(), stderr="")
+
+    monkeypatch.setattr(subprocess, "run", fake_subprocess_run)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "3", "--warmup", "3", "--watchdog", "300", *extra])
     bench.main()
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
@@ -74,7 +95,8 @@ def test_bench_main_dry_run(monkeypatch, capsys, extra):
     assert line["roofline"]["bound"] == "hbm" and 0 < line["roofline"]["frac"] and line["roofline"]["peak"] > 1000
     assert line["e2e"]["h2d_bytes_per_step"] == 2 * line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
-    if not extra:
+    if extra != ["--no-autotune", "--no-pipeline"]:
+        assert len(worker_calls) == (0 if extra else 1), line["config"]["autotune"]
         assert isinstance(line["config"]["autotune"], list) and len(line["config"]["autotune"]) >= 10
         assert line["config"]["autotune_rejected"] == []
         assert "host pipeline" in line["e2e"]["path"] or "note" in line["e2e"]

@@ -35,3 +35,31 @@ def test_autotune_candidates_are_bit_identical(name, domain):
     torch.cuda.synchronize()
     for fname in testing.written_fields(st):
         np.testing.assert_array_equal(dev[fname].get(), ref[fname], err_msg=f"{name}:{fname} {stencil.backend_options}")
+
+
+def test_isolated_autotune_adopts_a_verified_variant():
+    """the sweep in a sacrificial child process (gt4py_b200/tune_worker.py) on synthetic arguments of the
+    caller's geometry; the parent adopts the child's winner only after a bit-for-bit check on the real data"""
+    import torch
+
+    from gt4py_b200 import storage
+    from gt4py_b200.stencil import B200Stencil
+    from oracle import numpy_oracle
+
+    name, domain = "hdiff_f32", (200, 130, 3)
+    st = testing.load_ir(name, "staged")
+    fields, params, origins, domain = testing.make_case_data(st, name, domain=domain, seed=33)
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    dev = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+    stencil = B200Stencil(st, {"device_sync": False})
+    cands = [{}, {"interior_loop": True, "static_pitch": "auto"}, {"static_pitch": "auto"}, {"tile_j": 32}]
+    tuned = stencil.autotune_isolated(dev, params, domain=domain, origin=origins, candidates=cands, iters=3, timeout=240)
+    assert len(tuned) == 4 and stencil.tune_rejected == []
+    assert {k: v for k, v in stencil.backend_options.items() if k != "device_sync"} in [c for c, _ in tuned]
+    for fname in testing.written_fields(st):
+        dev[fname].fill(0)
+    stencil(**dev, **params, origin=origins, domain=domain)
+    torch.cuda.synchronize()
+    for fname in testing.written_fields(st):
+        np.testing.assert_array_equal(dev[fname].get(), ref[fname])
