@@ -106,7 +106,7 @@ def test_bench_main_dry_run(monkeypatch, capsys, extra):
         assert line["config"]["autotune"] is None and line["e2e"]["path"].startswith("serial")
 
 
-@pytest.mark.parametrize("workload", ["tridiagonal", "upwind5", "fastwaves"])
+@pytest.mark.parametrize("workload", ["tridiagonal", "upwind5", "fastwaves", "hdiff_x2", "hdiff_x2 --fuse"])
 def test_workload_bench_dry_run(monkeypatch, capsys, workload):
     import pathlib
 
@@ -123,9 +123,11 @@ def test_workload_bench_dry_run(monkeypatch, capsys, workload):
     monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
     monkeypatch.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
     monkeypatch.setattr(runtime.CompiledStencil, "run_descs", lambda self, d, s, dom, **kw: len(self.plan["kernels"]))
-    monkeypatch.setattr(bw, "cpu_baseline", lambda steps, halo: {"value": 1.0, "unit": "Mcell-updates/s", "cores": 1, "kind": "port", "sample": "stub"})
-    monkeypatch.setattr(sys, "argv", ["bench_workloads.py", "--workload", workload, "--steps", "3", "--shrink", "64"])
+    monkeypatch.setattr(bw, "cpu_baseline", lambda steps, halo, **kw: {"value": 1.0, "unit": "Mcell-updates/s", "cores": 1, "kind": "port", "sample": "stub"})
+    monkeypatch.setattr(sys, "argv", ["bench_workloads.py", "--workload", *workload.split(), "--steps", "3", "--shrink", "64"])
     bw.main()
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert line["n_gpus"] == 1 and line["gpu_launches"] > 0 and line["roofline"]["bytes_per_cell"] in (56, 16, 72)
+    assert line["n_gpus"] == 1 and line["gpu_launches"] > 0 and line["roofline"]["bytes_per_cell"] == {"tridiagonal": 56, "upwind5": 16, "fastwaves": 72, "hdiff_x2": 24, "hdiff_x2 --fuse": 12}[workload]
+    if workload.endswith("--fuse"):
+        assert line["gpu_launches"] == 3 and len(line["config"]["kernels"]) == 1  # one launch per pass of two updates
     assert "SMOKE RUN" in line["config"]["workload"] and line["cpu_baseline"]["kind"] == "port"

@@ -143,3 +143,26 @@ def test_artefacts_persist_in_gt_cache_and_warm_start_skips_codegen(gt, monkeypa
     assert runtime.CompiledStencil.load(st, {"strategy": "point"}, stem.parent, stem.stem) is None
     monkeypatch.setattr(jit, "_GEN_FP", "somethingelse")
     assert runtime.CompiledStencil.load(st, json.loads(m._B200_OPTS), stem.parent, stem.stem) is None
+
+
+@pytest.mark.needs_gt4py
+def test_fusing_two_gt4py_stencil_objects(tmp_path, monkeypatch):
+    """fuse.ir_of finds the IR of a `backend="b200"` StencilObject; the composed IR equals composing the
+    lowered definitions by hand."""
+    import numpy as np
+
+    from gt4py.cartesian import gtscript
+    from gt4py.cartesian.gtscript import PARALLEL, Field, computation, interval
+
+    from gt4py_b200 import fuse
+
+    def lap(u: Field[np.float64], out: Field[np.float64]):
+        with computation(PARALLEL), interval(...):
+            out = 4.0 * u - (u[1, 0, 0] + u[-1, 0, 0] + u[0, 1, 0] + u[0, -1, 0])
+
+    obj = gtscript.stencil(backend="b200", definition=lap, name="lap_for_fuse")
+    ir = fuse.ir_of(obj)
+    assert ir["t"] == "stencil" and set(ir["field_info"]) == {"u", "out"}
+    fused = fuse.compose("lap2", [(ir, {"out": "mid"}), (fuse.ir_of(obj), {"u": "mid"})], intermediates=["mid"])
+    assert fused["field_info"]["u"]["boundary"][:2] == [[2, 2], [2, 2]] and "mid" not in fused["field_info"]
+    assert [t["name"] for t in fused["temporaries"]][-1] == "mid"

@@ -76,3 +76,15 @@ def test_autotune_candidates_fit_a_cta(name, pitch):
         if cand.get("static_pitch") == "auto":
             cand["static_pitch"] = pitch
         _check(st, {"strategy": "auto", "device_sync": False, **cand}, codegen._cname(name))
+
+
+def test_fused_kernels_fit_a_cta():
+    """cross-stencil fusion doubles the register windows of a kernel: it must still launch and not spill"""
+    from gt4py_b200 import fuse
+
+    hd, up = testing.load_ir("hdiff_f32", "staged"), testing.load_ir("upwind5_f32", "staged")
+    for st in (fuse.repeat(hd, 2, carry=("in_field", "out_field")), fuse.repeat(hd, 3, carry=("in_field", "out_field")),
+               fuse.compose("hdiff_upwind", [(hd, {"out_field": "phi"}), (up, {})], intermediates=["phi"])):  # fmt: skip
+        for opts in ({}, {"interior_loop": True, "static_pitch": 1056}):
+            res = _check(st, opts, codegen._cname(st["name"]))
+            assert all(r["reg"] <= 168 for r in res.values()), res  # >= 3 CTAs of 4 warps per SM

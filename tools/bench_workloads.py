@@ -47,7 +47,26 @@ def workload(name: str, n_gpus: int):
                     rename={0: {"u_out": "u", "v_out": "v"}, 2: {"pp_out": "pp_new"}}, scaling="weak", dtype="f32",
                     label="fast-waves suite (pressure gradient, divergence, vertical implicit solve) 4096x512x80 fp32 per GPU "
                           "(BASELINE configs[4]: 4096x4096x80 per box of 8)")  # fmt: skip
+    if name == "hdiff_x2":
+        # two horizontal-diffusion time steps per pass (out of step 1 = in of step 2): as two calls (24 B per cell
+        # and pass) or, with --fuse, as ONE fused stencil (gt4py_b200/fuse.py: 12 B per cell and pass, the hand-over
+        # field lives in the register windows; step 1 is recomputed on a 2-cell rim of every tile)
+        return dict(stencils=[("hdiff_f32", "staged"), ("hdiff_f32", "staged")], domain=(1024, 1024, 80), halo=(4, 4, 0), exchanges={},
+                    rename={0: {"out_field": "mid"}, 1: {"in_field": "mid"}}, fuse_intermediates=["mid"], updates_per_step=2,
+                    scaling="weak", dtype="f32",
+                    label="2 x horizontal diffusion 1024x1024x80 fp32 per pass (temporal blocking of BASELINE configs[1]); N>1 = replicas")  # fmt: skip
     raise SystemExit(f"unknown workload {name}")
+
+
+def fused_description(w, steps):
+    """The whole step as ONE fused stencil."""
+    from gt4py_b200 import fuse
+
+    st = fuse.compose("_".join(dict.fromkeys(s["fixture"] for s in steps)) + f"_fused{len(steps)}",
+                      [(s["ir"], s["binding"]) for s in steps], intermediates=w.get("fuse_intermediates", []))  # fmt: skip
+    binding = {p["name"]: p["name"] for p in st["params"] if p["t"] == "field"}
+    return [dict(fixture=st["name"], variant="fused", ir=st, binding=binding, bytes_per_cell=testing.algorithmic_bytes_per_cell(st),
+                 params_from=[s["fixture"] for s in steps])]  # fmt: skip
 
 
 def step_description(w):
@@ -98,7 +117,7 @@ def default_params(st, fixture):
     return out
 
 
-def cpu_baseline(steps, halo, sample=(128, 128, 16)):
+def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
     from oracle import numpy_oracle
 
     rng = np.random.default_rng(0)
@@ -122,14 +141,15 @@ def cpu_baseline(steps, halo, sample=(128, 128, 16)):
         t0 = time.perf_counter()
         one()
         times.append(time.perf_counter() - t0)
-    cells = sample[0] * sample[1] * sample[2]
+    cells = sample[0] * sample[1] * sample[2] * updates
     return {"value": round(cells / float(np.median(times)) / 1e6, 3), "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
             "sample": f"oracle, {sample[0]}x{sample[1]}x{sample[2]} sub-domain, {len(times)} steps, median ({os.cpu_count()} host cores available, NumPy uses 1)"}  # fmt: skip
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", required=True, choices=["tridiagonal", "upwind5", "fastwaves"])
+    ap.add_argument("--workload", required=True, choices=["tridiagonal", "upwind5", "fastwaves", "hdiff_x2"])
+    ap.add_argument("--fuse", action="store_true", help="run the stencils of a step as one fused stencil (gt4py_b200/fuse.py)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
@@ -161,6 +181,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = workload(args.workload, world)
     steps = step_description(w)
+    if args.fuse:
+        if w["exchanges"] and world > 1:
+            raise SystemExit("--fuse: this workload exchanges halos between its stencils")
+        steps = fused_description(w, steps)
+        w["label"] += " [fused into one stencil]"
     ni, nj, nk = w["domain"]
     if args.shrink > 1:
         ni, nj = max(8, ni // args.shrink), max(8, nj // args.shrink)
@@ -239,7 +264,7 @@ def main():
     if clocks is not None:
         clocks.__exit__(None, None, None)
     ms = total_ms / args.steps
-    cells = ni * nj * nk * world
+    cells = ni * nj * nk * world * int(w.get("updates_per_step", 1))
     # kernels only, back to back (no exchange): the roofline numerator
     kt = []
     for _ in range(5):
@@ -271,7 +296,7 @@ def main():
             "clocks": clocks.summary() if clocks is not None else None,
         }  # fmt: skip
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline(steps, w["halo"])
+            line["cpu_baseline"] = cpu_baseline(steps, w["halo"], updates=int(w.get("updates_per_step", 1)))
         print(json.dumps(line))
     if exchanger is not None:
         exchanger.close()
