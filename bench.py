@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--strategy", default="auto")
     ap.add_argument("--overlap", action="store_true", help="N>1: always overlap the halo exchange with the interior tiles")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: always exchange first, then compute the whole slab")
+    ap.add_argument("--step-mode", default=None, choices=["serial", "overlap", "thin"],
+                    help="N>1: force one step schedule (default: a short trial of all of them, fastest on the max over ranks wins)")
     ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the default code-generation options")
@@ -252,8 +254,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     # N>1 default: time a few steps of both orders after the warm-up and keep the faster one (decided on
     # the max over ranks, so every rank takes the same decision)
-    args.overlap_mode = "on" if args.overlap else ("off" if args.no_overlap else "auto")
-    args.no_overlap = not args.overlap
+    args.step_mode = args.step_mode or ("overlap" if args.overlap else ("serial" if args.no_overlap else "auto"))
 
     # never hang the box: a lost peer / unmatched exchange turns into a loud non-zero exit
     def _abort():
@@ -352,34 +353,65 @@ def run_b200(args):
         ev_pool.append(e)
         return e
 
-    ev_ready, ev_halo = (make_event(), make_event()) if world > 1 else (None, None)
+    ev_ready, ev_halo, ev_strips = (make_event(), make_event(), make_event()) if world > 1 else (None, None, None)
+    # "thin" schedule: the boundary rows are computed by a short-tile variant of the same kernel (THIN rows per
+    # tile: a strip is one short wave instead of one full 64-row march) on a high-priority side stream, so they
+    # run as soon as the halo has arrived, concurrently with the tail of the interior kernel
+    THIN = 16
+    thin_frozen, strip_stream = None, None
+    if world > 1:
+        import ctypes
+
+        try:
+            thin = B200Stencil(st_ir, {**stencil.backend_options, "tile_j": THIN, "device_sync": False})
+            if thin.compiled.kernel_names() and all(k["kind"] == "stream" for k in thin.compiled.plan["kernels"]):
+                thin_frozen = thin.freeze(origin=origins, domain=domain)
+                h = ctypes.c_void_p()
+                runtime.check(lib.b200_stream_create_priority(ctypes.byref(h), 1))
+                strip_stream = int(h.value)
+        except Exception:
+            thin_frozen = None
+        # the schedule list must be the same on every rank (the trial below runs matched exchanges)
+        avail = torch.tensor([1.0 if thin_frozen is not None else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(avail, op=dist.ReduceOp.MIN)
+        if float(avail.item()) < 0.5:
+            thin_frozen = None
 
     launches = 0
+    mode = {"now": "serial"}
+
+    def start_exchange(bufs) -> int:
+        runtime.check(lib.b200_event_record(ev_ready, main_stream))
+        runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
+        n = exchanger.exchange([(bufs["in_field"], HALO, HALO)])
+        runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
+        return n
 
     def step(i: int) -> int:
         """one pass of the hot path over this rank's slab"""
         bufs = sets[i & 1]
         if exchanger is None:
             return frozen(**bufs)
-        n = 0
-        if args.no_overlap:
-            runtime.check(lib.b200_event_record(ev_ready, main_stream))
-            runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
-            n += exchanger.exchange([(bufs["in_field"], HALO, HALO)])
-            runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
+        n = start_exchange(bufs)
+        if mode["now"] == "serial":  # exchange, then the whole slab
             runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
             return n + frozen(**bufs)
-        # overlap: halo exchange on the comm stream || interior rows on the compute stream
-        runtime.check(lib.b200_event_record(ev_ready, main_stream))
-        runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev_ready))
-        n += exchanger.exchange([(bufs["in_field"], HALO, HALO)])
-        runtime.check(lib.b200_event_record(ev_halo, exchanger.stream))
-        # interior = all J tiles that do not touch a halo; the two boundary strips are whole 64-row
-        # tiles (not 2-row slivers), so they march at full efficiency and the split adds no GPU work
-        n += frozen(**bufs, subbox=(0, NI, STRIP, NJ - STRIP))
-        runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
-        n += frozen(**bufs, subbox=(0, NI, 0, STRIP))
-        n += frozen(**bufs, subbox=(0, NI, NJ - STRIP, NJ))
+        if mode["now"] == "overlap":
+            # halo exchange on the comm stream || interior rows on the compute stream; the two boundary strips
+            # are whole tiles of the tuned kernel (not 2-row slivers) launched behind the interior
+            n += frozen(**bufs, subbox=(0, NI, STRIP, NJ - STRIP))
+            runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
+            n += frozen(**bufs, subbox=(0, NI, 0, STRIP))
+            n += frozen(**bufs, subbox=(0, NI, NJ - STRIP, NJ))
+            return n
+        # "thin": interior on the compute stream; thin strips on the side stream behind the halo event only
+        runtime.check(lib.b200_stream_wait_event(strip_stream, ev_ready))
+        runtime.check(lib.b200_stream_wait_event(strip_stream, ev_halo))
+        n += frozen(**bufs, subbox=(0, NI, THIN, NJ - THIN))
+        n += thin_frozen(**bufs, subbox=(0, NI, 0, THIN), stream=strip_stream)
+        n += thin_frozen(**bufs, subbox=(0, NI, NJ - THIN, NJ), stream=strip_stream)
+        runtime.check(lib.b200_event_record(ev_strips, strip_stream))
+        runtime.check(lib.b200_stream_wait_event(main_stream, ev_strips))
         return n
 
     def barrier():
@@ -391,24 +423,44 @@ def run_b200(args):
         step(i)
     barrier()
     overlap_trial = None
-    if exchanger is not None and args.overlap_mode == "auto":
-        trial = {}
-        for mode in ("off", "on"):
-            args.no_overlap = mode == "off"
-            for i in range(2):
-                step(i)
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for i in range(6):
-                step(i)
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b) / 6], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            trial[mode] = round(float(t.item()), 5)
-        args.no_overlap = trial["off"] <= trial["on"]
-        overlap_trial = {"ms_per_step_no_overlap": trial["off"], "ms_per_step_overlap": trial["on"]}
+    if exchanger is not None:
+        modes = ["serial", "overlap"] + (["thin"] if thin_frozen is not None else [])
+        if args.step_mode != "auto":
+            if args.step_mode not in modes:
+                raise SystemExit(f"bench.py: step mode {args.step_mode} is not available for this kernel")
+            mode["now"] = args.step_mode
+        else:
+            # every schedule must reproduce the serial one bit for bit on this rank's data before it may be timed
+            expect, ok = None, {}
+            for m in modes:
+                mode["now"] = m
+                sets[0]["out_field"].fill(0)
+                step(0)
+                torch.cuda.synchronize()
+                got = sets[0]["out_field"].torch().clone()
+                if expect is None:
+                    expect = got
+                ok[m] = bool(torch.equal(got, expect))
+            flags = torch.tensor([1.0 if ok[m] else 0.0 for m in modes], device="cuda", dtype=torch.float64)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)  # a schedule is usable only if it is exact on every rank
+            usable = [m for m, f in zip(modes, flags.tolist()) if f > 0.5]
+            trial = {}
+            for m in usable:
+                mode["now"] = m
+                for i in range(2):
+                    step(i)
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(8):
+                    step(i)
+                b.record()
+                barrier()
+                t = torch.tensor([a.elapsed_time(b) / 8], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                trial[m] = round(float(t.item()), 5)
+            mode["now"] = min(trial, key=trial.get)
+            overlap_trial = {"ms_per_step": trial, "rejected_by_self_check": [m for m in modes if m not in usable]}
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
     # (clock sampling on rank 0 only: one nvidia-smi query stream for the whole job)
@@ -559,8 +611,9 @@ def run_b200(args):
                 "workload": f"horizontal diffusion (lap-of-lap + flux limiter) {NI}x{NJ}x{NK} fp32 per GPU "
                 f"(BASELINE configs[1]), literal_float_precision=32, fields {shape} origin {origin3}",
                 "parallelism": "single GPU" if n_gpus == 1 else f"J-slab decomposition x{n_gpus}, NCCL halo exchange "
-                + ("(no overlap)" if args.no_overlap else "overlapped with interior")
-                + (f"; order chosen by trial {overlap_trial}" if overlap_trial else ""),
+                + {"serial": "(exchange, then the whole slab)", "overlap": "overlapped with the interior tiles, whole-tile boundary strips behind",
+                   "thin": f"overlapped with the interior, {THIN}-row boundary strips on a high-priority side stream"}[mode["now"]]
+                + (f"; schedule chosen by trial {overlap_trial}" if overlap_trial else ""),
                 "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
                 "strategy": args.strategy,
                 "codegen_options": stencil.backend_options,

@@ -455,6 +455,14 @@ int b200_stream_create(void** stream) {
   *stream = s;
   return B200_OK;
 }
+int b200_stream_create_priority(void** stream, int high) {
+  int least = 0, greatest = 0;  // numerically lower = higher priority
+  CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  cudaStream_t s;
+  CU(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? greatest : least));
+  *stream = s;
+  return B200_OK;
+}
 int b200_stream_destroy(void* stream) {
   CU(cudaStreamDestroy((cudaStream_t)stream));
   return B200_OK;

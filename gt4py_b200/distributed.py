@@ -100,7 +100,8 @@ class HaloExchanger:
         runtime.check(lib.b200_comm_init(ctypes.byref(comm), idbuf, self.decomp.n_ranks, self.decomp.rank))
         self._comm = comm
         s = ctypes.c_void_p()
-        runtime.check(lib.b200_stream_create(ctypes.byref(s)))
+        # high priority: pack / NCCL / unpack get SM slots as soon as CTAs of a concurrently running stencil retire
+        runtime.check(lib.b200_stream_create_priority(ctypes.byref(s), 1))
         self._stream = s
         self._lib = lib
         self._torch = torch

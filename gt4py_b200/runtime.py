@@ -27,7 +27,7 @@ LIB_PATH = _PKG / "libgt4py_b200.so"
 EXPORTED_SYMBOLS = (
     "b200_abi_version", "b200_sizeof_field", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
     "b200_stencil_num_fields", "b200_stencil_scalars_size", "b200_stencil_num_kernels", "b200_stencil_kernel_name",
-    "b200_stencil_run", "b200_stream_create", "b200_stream_destroy", "b200_stream_synchronize",
+    "b200_stencil_run", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
     "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
     "b200_halo_exchange", "b200_pack_2d",
@@ -89,6 +89,7 @@ def load_library(build_if_missing: bool = True):
             "b200_stencil_kernel_name": (ctypes.c_char_p, [vp, ci]),
             "b200_stencil_run": (ci, [vp, ctypes.POINTER(B200Field), ci, vp, cz, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp]),
             "b200_stream_create": (ci, [pvp]),
+            "b200_stream_create_priority": (ci, [pvp, ci]),
             "b200_stream_destroy": (ci, [vp]),
             "b200_stream_synchronize": (ci, [vp]),
             "b200_event_create": (ci, [pvp]),

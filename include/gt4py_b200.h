@@ -83,6 +83,10 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
 
 /* ---- streams / events (device-side timing for exec_info and bench) --------------------------- */
 int b200_stream_create(void** stream);
+/* non-blocking stream with the highest (high != 0) or lowest scheduling priority of the device: halo exchange and
+ * boundary strips run on high-priority streams so that their small kernels get SM slots as soon as CTAs of the
+ * concurrently running interior kernel retire */
+int b200_stream_create_priority(void** stream, int high);
 int b200_stream_destroy(void* stream);
 int b200_stream_synchronize(void* stream);
 int b200_event_create(void** event);

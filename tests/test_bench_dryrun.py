@@ -131,3 +131,84 @@ def test_workload_bench_dry_run(monkeypatch, capsys, workload):
     if workload.endswith("--fuse"):
         assert line["gpu_launches"] == 3 and len(line["config"]["kernels"]) == 1  # one launch per pass of two updates
     assert "SMOKE RUN" in line["config"]["workload"] and line["cpu_baseline"]["kind"] == "port"
+
+
+@pytest.mark.parametrize("extra", [[], ["--step-mode", "thin"], ["--no-overlap"]])
+def test_bench_main_dry_run_two_ranks(monkeypatch, capsys, extra):
+    """the N>1 control flow of bench.py (schedule self-check, trial, matched step counts) with the device,
+    torch.distributed and the halo exchanger stubbed: rank 0 of a 2-rank job"""
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    from gt4py_b200 import distributed, runtime, storage
+
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setattr(bench, "NI", 64)
+    monkeypatch.setattr(bench, "NJ", 160)
+    monkeypatch.setattr(bench, "NK", 4)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda *a, **kw: real_tensor(*a, **{k: v for k, v in kw.items() if k != "device"}))
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **kw: None)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **kw: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, op=None: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **kw: None)
+    calls = {"exchange": 0, "subboxes": [], "streams": set()}
+
+    class FakeExchanger:
+        stream = 0x77
+
+        def __init__(self, decomp, local_nj):
+            assert decomp.n_ranks == 2 and local_nj == 160
+
+        def exchange(self, fields):
+            calls["exchange"] += 1
+            return 3
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(distributed, "HaloExchanger", FakeExchanger)
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def fn(*a):
+                import ctypes
+
+                if name in ("b200_event_create", "b200_stream_create_priority"):
+                    ctypes.cast(a[0], ctypes.POINTER(ctypes.c_void_p))[0] = 0x1000 + len(calls["streams"]) + 1
+                    calls["streams"].add(name + str(len(calls["streams"])))
+                return 0
+
+            return fn
+
+    monkeypatch.setattr(runtime, "load_library", lambda *a, **k: FakeLib())
+
+    def fake_run(self, descs, scalars, domain, *, stream=None, subbox=None):
+        calls["subboxes"].append((tuple(subbox) if subbox is not None else None, self.options.get("tile_j"), stream))
+        return len(self.plan["kernels"])
+
+    monkeypatch.setattr(runtime.CompiledStencil, "run_descs", fake_run)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "2", "--steps", "3", "--warmup", "3", "--no-autotune", "--no-pipeline", *extra])
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2 and "cpu_baseline" not in line and calls["exchange"] > 6
+    par = line["config"]["parallelism"]
+    thin_strips = [c for c in calls["subboxes"] if c[0] in ((0, 64, 0, 16), (0, 64, 144, 160))]
+    if extra == ["--no-overlap"]:
+        assert "then the whole slab" in par and not thin_strips and line["gpu_launches"] == 3 * (3 + 1)
+    elif extra:
+        assert "16-row boundary strips" in par and thin_strips and line["gpu_launches"] == 3 * (3 + 3)
+        assert all(tj == 16 and stream is not None for _, tj, stream in thin_strips)  # short-tile kernel, side stream
+        assert ((0, 64, 16, 144), None, None) in calls["subboxes"]  # interior: the tuned kernel on the compute stream
+    else:
+        assert "schedule chosen by trial" in par and set(line["config"]["parallelism"].split("'ms_per_step': ")[1][:80].replace("'", '"').split('"')[1::2]) >= {"serial", "overlap", "thin"}

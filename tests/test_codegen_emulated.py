@@ -101,6 +101,24 @@ def test_subbox_launches_compose(name, variant, strategy):
         run_emulated(name, variant, tuned, domain=(ni, nj, 2), seed=5, subboxes=boxes, layout="b200", guard="end")
 
 
+@pytest.mark.parametrize("tuned", [{}, {"interior_loop": True, "static_pitch": 96}, {"vector_width": 4}])
+def test_thin_strip_schedule_composes_two_kernel_variants(tuned):
+    """bench.py's "thin" multi-GPU schedule: interior rows by the tuned kernel, the two 16-row boundary strips
+    by the tile_j=16 variant of the same kernel (side stream on the device) == the whole-domain result"""
+    st = testing.load_ir("hdiff_f32", "staged")
+    ni, nj, thin = 70, 150, 16
+    fields, params, origins, domain = testing.make_case_data(st, "hdiff_f32", domain=(ni, nj, 2), seed=8)
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    EmuStencil(st, {"strategy": "auto", **tuned}, name="hdiff_f32.staged").run(
+        fields, params, domain, origins, subbox=(0, ni, thin, nj - thin), layout="b200", guard="end")
+    strips = EmuStencil(st, {"strategy": "auto", **tuned, "tile_j": thin}, name="hdiff_f32.staged")
+    assert strips.plan["kernels"][0]["tile"][1] == thin
+    for box in ((0, ni, 0, thin), (0, ni, nj - thin, nj)):
+        strips.run(fields, params, domain, origins, subbox=box, layout="b200", guard="end")
+    compare("hdiff_f32", "out_field", fields["out_field"], ref["out_field"])
+
+
 @pytest.mark.parametrize(
     "opts",
     [
