@@ -506,11 +506,14 @@ def run_b200(args):
     kernel_ms = float(np.mean(kt))
     peak, peak_src = measured_peaks()
     achieved = NI * NJ * NK * BYTES_PER_CELL / kernel_ms / 1e6  # GB/s
-    traffic = None
+    # DRAM traffic per launch: from the committed ncu capture, which is of the DEFAULT code-generation variant
+    # (the tuned variants move the same rows through the same L2-prefetched streams; re-captured per round)
+    traffic, traffic_src = None, None
     tr = ROOT / "profiles" / "hdiff_traffic.json"
     if tr.exists():
         try:
-            traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tr.read_text())
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             traffic = None
 
@@ -630,6 +633,7 @@ def run_b200(args):
                 "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
                 "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "kernel_ms": round(kernel_ms, 5),
                 "algorithmic_bytes_per_launch": NI * NJ * NK * BYTES_PER_CELL,

@@ -421,7 +421,7 @@ class B200Stencil:
         # `refine` rounds) so that the choice among near-equal variants is not a coin toss
         if refine and len(results) > 1:
             top = results[: min(6, len(results))]
-            best_ms = {id(r[2]): r[1] for r in top}
+            best_ms = {id(r[2]): float("inf") for r in top}  # only the interleaved re-timings rank the leaders
             for _ in range(int(refine)):
                 for cand, _ms, cs, _opts in top:
                     scal, descs = cs.pack_scalars(params), cs.make_field_descs(views, origin)
