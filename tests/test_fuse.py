@@ -203,3 +203,49 @@ def test_extent_analysis_reproduces_the_reference_on_every_fixture(name, variant
         e = need[fname]
         got = [[-e[0][0], e[0][1]] if "I" in fi["axes"] else [0, 0], [-e[1][0], e[1][1]] if "J" in fi["axes"] else [0, 0]]
         assert got == [list(b) for b in fi["boundary"][:2]], fname
+
+
+def _fusable_pairs(n, seed):
+    """seeded sample of (producer fixture, consumer fixture, written field, read field) with matching dtypes"""
+    import random
+
+    pool = []
+    for name in testing.list_cases():
+        st = testing.load_ir(name, "staged")
+        if _has_hregion(st) or "while" in name or name in ("math_f64", "math_f32", "rounding_f64") or "varoff" in name:
+            continue
+        pool.append((name, st))
+    rng = random.Random(seed)
+    pairs = [(a, b) for a in pool for b in pool]
+    rng.shuffle(pairs)
+    out = []
+    for (na, a), (nb, b) in pairs:
+        wa = [n for n, fi in a["field_info"].items() if fi and fi["access"] == "WRITE" and len(fi["axes"]) == 3 and not fi["data_dims"]]
+        rb = [n for n, fi in b["field_info"].items()
+              if fi and fi["access"] == "READ" and len(fi["axes"]) == 3 and not fi["data_dims"] and tuple(fi["boundary"][2]) == (0, 0)]  # fmt: skip
+        ok = [(x, y) for x in wa for y in rb if a["field_info"][x]["dtype"] == b["field_info"][y]["dtype"]]
+        if ok:
+            out.append((na, nb, *rng.choice(ok)))
+        if len(out) == n:
+            break
+    return out
+
+
+@pytest.mark.parametrize("na,nb,x,y", _fusable_pairs(14, seed=2026))
+def test_random_fixture_pairs_fused(na, nb, x, y):
+    """differential check of the generators on fused IRs (seeded sample of what /tmp fuzzing ran 190 pairs of):
+    producer.x -> consumer.y as an intermediate; emulated kernels (storage layout, guard pages) == oracle"""
+    a, b = testing.load_ir(na, "staged"), testing.load_ir(nb, "staged")
+    bind_b = {n: "b_" + n for n in [p["name"] for p in b["params"]] + list(b["field_info"]) + list(b["parameter_info"])}
+    bind_b[y] = "handover"
+    fused = fuse.compose(f"fz_{na}_{nb}", [(a, {x: "handover"}), (b, bind_b)], intermediates=["handover"])
+    domain = (37, 9, max(4, int(fused["domain_info"]["min_k"])))
+    fields, params, origins, domain = testing.make_case_data(fused, fused["name"], domain=domain, seed=11)  # no fixture recipe
+    ref = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
+    with np.errstate(all="ignore"):
+        numpy_oracle.run(fused, ref, params, domain, origins)
+    for opts in ({"strategy": "auto"}, {"strategy": "point"}):
+        got = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
+        EmuStencil(fused, opts, name=fused["name"]).run(got, params, domain, origins, layout="b200", guard="end")
+        for n in testing.written_fields(fused):
+            np.testing.assert_array_equal(got[n], ref[n], err_msg=f"{na}->{nb} {opts}: {n}")
