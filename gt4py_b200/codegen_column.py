@@ -325,9 +325,20 @@ class ColumnKernel:
         gen.live |= {a["name"] for he in self.hes for a in b2ir.field_accesses(he["body"])}
         gen.kernels.append(
             {"name": name, "kind": "seq", "block": [bx, by, 1], "extent": [list(self.extent[0]), list(self.extent[1])],
-             "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": 0}
+             "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": self._smem_pad()}
         )  # fmt: skip
         return len(gen.kernels) - 1
+
+    def _smem_pad(self) -> int:
+        """`seq_smem_pad` = bytes of (unused) dynamic shared memory requested per CTA: caps the resident CTAs per SM
+        (227 KB / pad) without touching the code.  For fused sweeps (`fuse_columns`) fewer resident columns keep a
+        column's forward-sweep results in L2 until its back substitution re-reads them (2.5 KB per column for the
+        Thomas solver at nK=160: 126 MB of L2 hold ~50 K columns = 10 warps per SM), trading occupancy — made up
+        by a deeper `seq_prefetch` — for 72 -> 56 B/cell of HBM traffic.  To be measured."""
+        pad = int(self.opts.get("seq_smem_pad", 0) or 0)
+        if not 0 <= pad <= 227 * 1024:
+            raise ValueError("seq_smem_pad must be between 0 and 232448 bytes")
+        return pad
 
 
 def fusable(a: dict, b: dict) -> bool:

@@ -37,7 +37,13 @@ def main():
         {"interior_loop": True, "static_pitch": PITCH, "l2_prefetch": 4},
     ]  # fmt: skip
     col_variants = [{"seq_cache": False}, {"seq_prefetch": 0}, {}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"fuse_columns": True},
-                    {"fuse_columns": True, "seq_prefetch": 2}]  # fmt: skip
+                    {"fuse_columns": True, "seq_prefetch": 2},
+                    # fused sweeps with the resident columns capped so that a column's forward results are still in L2
+                    # when its back substitution re-reads them (2 / 3 / 4 CTAs per SM), deeper look-ahead to make up
+                    {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 110 * 1024},
+                    {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 75 * 1024},
+                    {"fuse_columns": True, "seq_prefetch": 6, "seq_smem_pad": 110 * 1024},
+                    {"fuse_columns": True, "seq_prefetch": 3, "seq_smem_pad": 56 * 1024}]  # fmt: skip
     runs = []
     for v in stream_variants:
         runs.append(("hdiff_f32", "staged", (1024 // q, 1024 // q, 80), v))  # config 2
