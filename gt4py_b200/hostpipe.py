@@ -86,7 +86,7 @@ class PinnedMirror:
 
         self.dev = dev
         self.flat = torch.empty(dev._base.numel(), dtype=dev._base.dtype).pin_memory()
-        self._view = torch.as_strided(self.flat, dev.shape, dev.element_strides, dev._offset)
+        self._view = torch.as_strided(self.flat, dev.shape, dev.element_strides, self.flat.storage_offset() + dev._offset)
         if src is not None:
             self._view.copy_(torch.from_numpy(np.ascontiguousarray(src)))
 

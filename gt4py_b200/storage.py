@@ -203,7 +203,9 @@ class DeviceArray:
 
     def torch(self):
         """Zero-copy strided torch view."""
-        return _torch().as_strided(self._base, self.shape, self._estrides, self._offset)
+        # as_strided offsets count from the start of the underlying storage: add the base view's own offset
+        # (non-zero whenever the allocation had to be shifted to reach the requested alignment)
+        return _torch().as_strided(self._base, self.shape, self._estrides, self._base.storage_offset() + self._offset)
 
     def get(self) -> np.ndarray:
         """Copy to host (like cupy.ndarray.get)."""
@@ -214,7 +216,8 @@ class DeviceArray:
         return out.astype(dtype) if dtype is not None else out
 
     def _view(self, t) -> "DeviceArray":
-        return DeviceArray(self._base, t.storage_offset(), tuple(t.shape), tuple(t.stride()), self.dtype)
+        # offsets of DeviceArray are relative to `_base`, torch's to the start of the storage
+        return DeviceArray(self._base, t.storage_offset() - self._base.storage_offset(), tuple(t.shape), tuple(t.stride()), self.dtype)
 
     def __getitem__(self, key):
         return self._view(self.torch()[key])

@@ -22,8 +22,36 @@ def _have_gpu():
         return False
 
 
+EMULATE = __import__("os").environ.get("B200_EMULATE_DEVICE") == "1"
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _emulated_device():
+    """B200_EMULATE_DEVICE=1: the `-m gpu` tests run on a fake device (tests/emu/fake_device.py) so that their
+    own logic can be checked where there is no GPU."""
+    if not EMULATE or _have_gpu():
+        yield
+        return
+    from emu import fake_device
+
+    mp = pytest.MonkeyPatch()
+    fake_device.install(mp)
+    yield
+    mp.undo()
+
+
 def pytest_collection_modifyitems(config, items):
     gpu = _have_gpu()
+    if EMULATE and not gpu:
+        from emu import fake_device
+
+        skip_emu = pytest.mark.skip(reason="needs real device behaviour (not emulated)")
+        for item in items:
+            if "gpu" in item.keywords and any(s in item.nodeid for s in fake_device.SKIP):
+                item.add_marker(skip_emu)
+            elif "gpu" not in item.keywords and any(s in item.nodeid for s in fake_device.SKIP):
+                item.add_marker(skip_emu)
+        gpu = True
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
     skip_gt = pytest.mark.skip(reason="gt4py frontend not importable here")
     for item in items:

@@ -1,0 +1,120 @@
+"""`B200_EMULATE_DEVICE=1 pytest -m gpu`: run the GPU test-suite's LOGIC on the CPU (test infrastructure only).
+
+The `-m gpu` tests can only be run on the B200 box, where a bug in a test (not in the product) would stop
+the suite under `-x`.  This module stands a fake device under them: storages live in host memory (same pitched
+layout), every `b200_stencil_run` is executed by the CPU emulator of the generated kernels (tests/emu/emu.py)
+on the very pointers / strides / origins the launcher would receive, streams and events are no-ops.  It says
+nothing about the device; it checks data flow, shapes, argument plumbing and assertions of the tests
+themselves.  Tests that need real device behaviour (CUDA graphs, full-size domains, child processes) skip.
+"""
+
+from __future__ import annotations
+
+import contextlib
+import ctypes
+
+import numpy as np
+
+SKIP = ("test_zz_graph_gpu", "test_hdiff_full_size_properties", "test_isolated_autotune", "test_no_cpu_fallback")
+
+
+class _Event:
+    clock = 0.0
+
+    def __init__(self, enable_timing=False):
+        self.at = 0.0
+
+    def record(self, stream=None):
+        _Event.clock += 0.25
+        self.at = _Event.clock
+
+    def synchronize(self):
+        pass
+
+    def elapsed_time(self, other):
+        return max(other.at - self.at, 0.01)
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, event):
+        pass
+
+
+def _array_from_desc(desc, f):
+    dtype = np.dtype("bool" if f["dtype"] == "bool" else f["dtype"])
+    dims = [a for a in range(3) if f["dims"][a]]
+    shape = [int(desc.shape[a]) for a in dims] + [int(d) for d in f["data_dims"]]
+    strides = [int(desc.strides[a]) for a in dims] + [int(desc.strides[3 + d]) for d in range(len(f["data_dims"]))]
+    origin = [int(desc.origin[a]) for a in dims] + [0] * len(f["data_dims"])
+    span = 1 + sum((n - 1) * s for n, s in zip(shape, strides))
+    buf = (ctypes.c_char * (span * dtype.itemsize)).from_address(int(desc.data))
+    arr = np.ndarray(shape, dtype, buffer=buf, strides=[s * dtype.itemsize for s in strides])
+    return arr, tuple(origin)
+
+
+def install(mp) -> None:
+    """mp: a pytest.MonkeyPatch"""
+    import torch
+
+    from gt4py_b200 import runtime, storage
+
+    from .emu import EmuStencil
+
+    mp.setattr(torch.cuda, "is_available", lambda: True)
+    mp.setattr(torch.cuda, "set_device", lambda d: None)
+    mp.setattr(torch.cuda, "synchronize", lambda *a: None)
+    mp.setattr(torch.cuda, "current_stream", lambda *a: _Stream())
+    mp.setattr(torch.cuda, "Event", _Event)
+    mp.setattr(torch.cuda, "Stream", _Stream)
+    mp.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    mp.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    mp.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    mp.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
+
+    real_as_view = runtime.as_view
+
+    def as_view(obj):
+        if type(obj).__module__.startswith("torch") and not isinstance(obj, runtime.ArrayView):
+            np_dtype = np.dtype(str(obj.dtype).replace("torch.", ""))
+            return runtime.ArrayView(obj.data_ptr(), obj.shape, obj.stride(), np_dtype, obj)
+        return real_as_view(obj)
+
+    mp.setattr(runtime, "as_view", as_view)
+
+    def run_descs(self, descs, scalars, domain, *, stream=None, subbox=None):
+        target = self.specialized_for(descs)
+        emu = getattr(target, "_emu", None)
+        if emu is None:
+            emu = target._emu = EmuStencil(target.ir, target.options, name=target.name)
+        fields, origins = {}, {}
+        for n, f in enumerate(target._api):
+            d = descs[n]
+            if not d.data:
+                fields[f["name"]] = None
+                continue
+            fields[f["name"]], origins[f["name"]] = _array_from_desc(d, f)
+        vals = target._scal_struct.unpack(scalars) if target._scalars else ()
+        params = {s["name"]: v for s, v in zip(target._scalars, vals)}
+        before = emu.launches
+        emu.run(fields, params, tuple(int(x) for x in domain), origins, subbox=tuple(subbox) if subbox is not None else None)
+        self.last_launches = emu.launches - before
+        return self.last_launches
+
+    mp.setattr(runtime.CompiledStencil, "run_descs", run_descs)
+
+    real_lib = runtime.load_library()
+
+    class Lib:
+        def __getattr__(self, name):
+            if name.startswith(("b200_stream_", "b200_event_")):
+                return lambda *a: 0
+            if name.startswith(("b200_graph_", "b200_comm_", "b200_halo_", "b200_pack_")):
+                raise AssertionError(f"{name} needs a real device")
+            return getattr(real_lib, name)
+
+    mp.setattr(runtime, "load_library", lambda *a, **k: Lib())
