@@ -15,7 +15,7 @@ import ctypes
 
 import numpy as np
 
-SKIP = ("test_capture_before_first_call_fails_loudly", "test_hdiff_full_size_properties", "test_no_cpu_fallback",
+SKIP = ("test_capture_before_first_call_fails_loudly", "test_no_cpu_fallback",
         "test_gt_dims_permutation")  # (__cuda_array_interface__ of a host tensor)
 
 
