@@ -124,6 +124,14 @@ def install(mp) -> None:
             ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x5000
             return 0
 
+        def b200_stream_create_priority(self, ref, high):
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x5100
+            return 0
+
+        def b200_event_create(self, ref):
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x6000
+            return 0
+
         def b200_graph_begin(self, stream):
             capture["on"], capture["calls"] = True, []
             return 0
