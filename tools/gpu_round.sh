@@ -27,8 +27,9 @@ step 900  tests_gpu  python -m pytest tests -q -m gpu -x --durations=15
 # launch list of the bench command (per-launch times are cold-cache / serialised: shares, not absolutes)
 step 420  ncu_list   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches_bench.csv" \
                      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --tune-in-process
-# full capture of the tuned headline kernel (one launch) and of the fused two-step kernel
-step 420  ncu_hdiff  ncu --set full --clock-control none --import-source on -k regex:b200_hdiff_f32_stream0 -s 60 -c 1 -f -o "$OUT/${TAG}_hdiff_tuned" \
+# full capture of the tuned headline kernel (launch 1500 of that name: past the autotune sweep, inside the steady stepping loop)
+# and of the fused two-step kernel
+step 420  ncu_hdiff  ncu --set full --clock-control none --import-source on -k regex:b200_hdiff_f32_stream0 -s 1500 -c 1 -f -o "$OUT/${TAG}_hdiff_tuned" \
                      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --tune-in-process
 step 300  ncu_fused  ncu --set full --clock-control none --import-source on -k regex:fused2_stream0 -s 4 -c 1 -f -o "$OUT/${TAG}_hdiff_fused2" \
                      python tools/bench_workloads.py --workload hdiff_x2 --fuse --steps 3 --warmup 3
