@@ -76,7 +76,8 @@ class HaloExchanger:
         self.local_nj = decomp.local_nj if local_nj is None else local_nj
         self.transport = transport
         self._comm = None
-        self._stage: Dict[Any, Any] = {}
+        self._plans: Dict[Any, Any] = {}
+        self._stage_device = "cuda"
         self._stream = None
         if transport == "nccl":
             self._init_nccl()
@@ -126,23 +127,22 @@ class HaloExchanger:
         # layout (2,0,1): J outermost -> one contiguous chunk
         return view.ptr + j0 * sj * item, 1, h * sj * item, h * sj * item
 
-    def exchange(self, fields: Sequence[Tuple[Any, int, int]], *, stream: Optional[int] = None) -> int:
-        """Enqueue pack -> NCCL send/recv -> unpack for all fields on `stream` (default: own stream).
-        Returns the number of kernels launched (pack/unpack), NCCL calls not counted."""
-        if self.transport != "nccl":
-            raise RuntimeError("exchange() is the device path; use exchange_host() with the gloo transport")
+    def _exchange_plan(self, views):
+        """Everything one exchange of these buffers needs, prepared once per (pointer, geometry) set: the
+        `b200_halo_t` array for the NCCL group, the argument tuples of the pack / unpack launches and the
+        staging buffers.  The per-step cost of `exchange()` is then a handful of C calls."""
         from . import runtime
 
-        lib, torch = self._lib, self._torch
-        st = self.stream if stream is None else stream
-        d = self.decomp
-        halos = (runtime.B200Halo * max(1, len(fields)))()
-        launches = 0
-        unpack: List[Tuple] = []
-        for n, (arr, oj, h) in enumerate(fields):
-            view = runtime.as_view(arr)
-            key = (view.ptr, view.shape, view.strides, oj, h)
-            stage = self._stage.get(key)
+        key = tuple((v.ptr, v.shape, v.strides, oj, h) for v, oj, h in views)
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        torch, d = self._torch, self.decomp
+        halos = (runtime.B200Halo * max(1, len(views)))()
+        packs: List[Tuple] = []
+        unpacks: List[Tuple] = []
+        keep = []
+        for n, (view, oj, h) in enumerate(views):
             specs = {
                 "send_lo": self._slab_spec(view, oj, h),
                 "send_hi": self._slab_spec(view, oj + self.local_nj - h, h),
@@ -150,28 +150,43 @@ class HaloExchanger:
                 "recv_hi": self._slab_spec(view, oj + self.local_nj, h),
             }
             nbytes = specs["send_lo"][1] * specs["send_lo"][2]
-            if stage is None:
-                stage = {k: torch.empty(nbytes, dtype=torch.uint8, device="cuda") for k in specs}
-                self._stage[key] = stage
+            stage = {k: torch.empty(nbytes, dtype=torch.uint8, device=self._stage_device) for k in specs}
+            keep.append(stage)
             hd = halos[n]
             hd.bytes = nbytes
             for side, peer in (("lo", d.peer_lo), ("hi", d.peer_hi)):
+                if peer < 0:
+                    continue
                 ptr, rows, row_bytes, pitch = specs[f"send_{side}"]
-                if peer >= 0:
-                    if rows > 1:
-                        runtime.check(lib.b200_pack_2d(stage[f"send_{side}"].data_ptr(), row_bytes, ptr, pitch, row_bytes, rows, st))
-                        launches += 1
-                        setattr(hd, f"send_{side}", stage[f"send_{side}"].data_ptr())
-                        setattr(hd, f"recv_{side}", stage[f"recv_{side}"].data_ptr())
-                        unpack.append((specs[f"recv_{side}"], stage[f"recv_{side}"].data_ptr()))
-                    else:
-                        setattr(hd, f"send_{side}", ptr)
-                        setattr(hd, f"recv_{side}", specs[f"recv_{side}"][0])
-        runtime.check(lib.b200_halo_exchange(self._comm, halos, len(fields), d.peer_lo, d.peer_hi, st))
-        for (ptr, rows, row_bytes, pitch), src in unpack:
-            runtime.check(lib.b200_pack_2d(ptr, pitch, src, row_bytes, row_bytes, rows, st))
-            launches += 1
-        return launches
+                if rows > 1:  # strided slab (layout (2,1,0): nK chunks): staged through a contiguous buffer
+                    packs.append((stage[f"send_{side}"].data_ptr(), row_bytes, ptr, pitch, row_bytes, rows))
+                    setattr(hd, f"send_{side}", stage[f"send_{side}"].data_ptr())
+                    setattr(hd, f"recv_{side}", stage[f"recv_{side}"].data_ptr())
+                    rptr, rrows, rrow_bytes, rpitch = specs[f"recv_{side}"]
+                    unpacks.append((rptr, rpitch, stage[f"recv_{side}"].data_ptr(), rrow_bytes, rrow_bytes, rrows))
+                else:  # contiguous slab: sent / received in place
+                    setattr(hd, f"send_{side}", ptr)
+                    setattr(hd, f"recv_{side}", specs[f"recv_{side}"][0])
+        plan = (halos, packs, unpacks, keep)
+        self._plans[key] = plan
+        return plan
+
+    def exchange(self, fields: Sequence[Tuple[Any, int, int]], *, stream: Optional[int] = None) -> int:
+        """Enqueue pack -> NCCL send/recv -> unpack for all fields on `stream` (default: own stream).
+        Returns the number of kernels launched (pack/unpack), NCCL calls not counted."""
+        if self.transport != "nccl":
+            raise RuntimeError("exchange() is the device path; use exchange_host() with the gloo transport")
+        from . import runtime
+
+        lib = self._lib
+        st = self.stream if stream is None else stream
+        halos, packs, unpacks, _keep = self._exchange_plan([(runtime.as_view(arr), oj, h) for arr, oj, h in fields])
+        for args in packs:
+            runtime.check(lib.b200_pack_2d(*args, st))
+        runtime.check(lib.b200_halo_exchange(self._comm, halos, len(fields), self.decomp.peer_lo, self.decomp.peer_hi, st))
+        for args in unpacks:
+            runtime.check(lib.b200_pack_2d(*args, st))
+        return len(packs) + len(unpacks)
 
     # -- host transport (gloo) for CPU tests of the indexing logic ----------------------------------
     def exchange_host(self, fields: Sequence[Tuple[np.ndarray, int, int]]) -> None:
