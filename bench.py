@@ -326,9 +326,9 @@ def run_b200(args):
         # or hangs on the device cannot take this process' CUDA context, and with it the bench line.
         try:
             if args.tune_in_process:
-                tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins)
+                tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins, iters=20)
             else:
-                tuned = stencil.autotune_isolated(sets[0], {}, domain=domain, origin=origins, timeout=min(240.0, args.watchdog / 2), device=local_rank)
+                tuned = stencil.autotune_isolated(sets[0], {}, domain=domain, origin=origins, iters=20, timeout=min(240.0, args.watchdog / 2), device=local_rank)
         except Exception as exc:  # keep the measured default rather than lose the bench line
             tuned = f"autotune failed, default options used: {type(exc).__name__}: {str(exc)[-400:]}"
     frozen = stencil.freeze(origin=origins, domain=domain)
