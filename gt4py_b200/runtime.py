@@ -65,6 +65,8 @@ _lib_lock = threading.Lock()
 def load_library(build_if_missing: bool = True):
     """dlopen libgt4py_b200.so (building it in-tree first if it is missing and nvcc exists)."""
     global _lib
+    if _lib is not None:  # fast path of every launch: no lock once loaded
+        return _lib
     with _lib_lock:
         if _lib is not None:
             return _lib
@@ -244,6 +246,7 @@ class CompiledStencil:
         self._scalars = self.plan["scalars"]
         self._scal_struct = self._make_scalar_packer()
         self.last_launches = 0
+        self._dom_cache: Dict[Any, Any] = {}  # domain / sub-box tuples -> ctypes arrays (the launch path is hot)
 
     def _make_scalar_packer(self):
         fmt_of = {"bool": "?", "int8": "b", "int16": "h", "int32": "i", "int64": "q", "float32": "f", "float64": "d"}
@@ -389,8 +392,18 @@ class CompiledStencil:
             self.last_launches = n
             return n
         lib = load_library()
-        dom = (ctypes.c_int32 * 3)(*[int(d) for d in domain])
-        sb = (ctypes.c_int32 * 4)(*[int(x) for x in subbox]) if subbox is not None else None
+        domain = tuple(domain)
+        dom = self._dom_cache.get(domain)
+        if dom is None:
+            if len(self._dom_cache) > 64:
+                self._dom_cache.clear()
+            dom = self._dom_cache[domain] = (ctypes.c_int32 * 3)(*[int(d) for d in domain])
+        sb = None
+        if subbox is not None:
+            bkey = ("box", *subbox)
+            sb = self._dom_cache.get(bkey)
+            if sb is None:
+                sb = self._dom_cache[bkey] = (ctypes.c_int32 * 4)(*[int(x) for x in subbox])
         if stream is None:
             stream = current_stream_handle()
         n = check(lib.b200_stencil_run(self.handle, descs, len(self._api), scalars, len(scalars), dom, sb, ctypes.c_void_p(stream)))

@@ -530,26 +530,57 @@ class FrozenStencil:
         self.stencil_object = stencil
         self.origin = origin
         self.domain = domain
-        self._key = None
-        self._descs = None
+        # argument objects -> prepared descriptors.  Keyed by object identity (the entry holds the objects, so an id
+        # cannot be recycled while it is cached) and re-validated against the arguments' pointers: a model step
+        # calls with the same few buffer sets over and over, and this path is what it pays per launch.
+        self._cache: Dict[tuple, tuple] = {}
         self._scal_key = None
         self._scal = None
+        self._names = tuple(stencil._field_names)
+        self._pnames = tuple(stencil._param_names)
+
+    def _descs_for(self, kwargs):
+        st = self.stencil_object
+        args = tuple(kwargs.get(n) for n in self._names)
+        ids = tuple(map(id, args))
+        hit = self._cache.get(ids)
+        if hit is not None:
+            descs, held, ptrs = hit
+            # same objects: geometry can only have changed if a tensor was re-pointed in place
+            if all(a is h for a, h in zip(args, held)) and ptrs == tuple((_ptr_of(a), getattr(a, "shape", None)) for a in args):
+                return descs
+        views = {n: (runtime.as_view(a) if a is not None else None) for n, a in zip(self._names, args)}
+        descs = st.compiled.make_field_descs(views, self.origin)
+        if len(self._cache) >= 16:
+            self._cache.clear()
+        self._cache[ids] = (descs, args, tuple((_ptr_of(a), getattr(a, "shape", None)) for a in args))
+        return descs
 
     def __call__(self, *, exec_info=None, stream=None, subbox=None, **kwargs) -> int:
         st = self.stencil_object
-        views = {n: (runtime.as_view(kwargs[n]) if kwargs.get(n) is not None else None) for n in st._field_names}
-        key = tuple((v.ptr, v.shape, v.strides) if v is not None else None for v in views.values())
-        if key != self._key:
-            self._descs = st.compiled.make_field_descs(views, self.origin)
-            self._key = key
-        skey = tuple(kwargs.get(n) for n in st._param_names)
-        if skey != self._scal_key:
-            self._scal = st.compiled.pack_scalars({n: kwargs.get(n) for n in st._param_names})
-            self._scal_key = skey
-        n = st.compiled.run_descs(self._descs, self._scal, self.domain, stream=stream, subbox=subbox)
+        descs = self._descs_for(kwargs)
+        if self._pnames:
+            skey = tuple(kwargs.get(n) for n in self._pnames)
+            if skey != self._scal_key:
+                self._scal = st.compiled.pack_scalars({n: kwargs.get(n) for n in self._pnames})
+                self._scal_key = skey
+        elif self._scal is None:
+            self._scal = st.compiled.pack_scalars({})
+        n = st.compiled.run_descs(descs, self._scal, self.domain, stream=stream, subbox=subbox)
         if st.device_sync:
             runtime.check(runtime.load_library().b200_stream_synchronize(stream if stream is not None else runtime.current_stream_handle()))
         return n
+
+
+def _ptr_of(obj) -> int:
+    """cheap identity of the memory an argument points at (no view construction)"""
+    if obj is None:
+        return 0
+    dp = getattr(obj, "data_ptr", None)
+    if dp is not None:
+        return dp() if callable(dp) else dp
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    return int(cai["data"][0]) if cai is not None else id(obj)
 
 
 def _strides_follow_layout(strides, dims) -> bool:

@@ -195,3 +195,56 @@ def test_stencil_graph_control_flow_with_a_stubbed_launcher(monkeypatch):
     assert runtime.current_stream_handle() == 0 and log[-1] == ("destroy", 0x7000)
     with pytest.raises(runtime.B200Error, match="nothing captured"):
         g2.launch()
+
+
+def test_frozen_stencil_descriptor_cache(monkeypatch):
+    """FrozenStencil keeps prepared descriptors per set of argument objects (re-validated against their pointers
+    and shapes): alternating buffer sets hit the cache, a re-pointed tensor does not, scalars are repacked on change."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from gt4py_b200 import storage, testing
+    from gt4py_b200.stencil import B200Stencil
+
+    seen = []
+
+    class Lib:
+        def b200_stencil_run(self, handle, descs, nfields, scalars, nbytes, dom, sb, stream):
+            seen.append(([int(descs[n].data or 0) for n in range(nfields)], bytes(scalars), tuple(dom), None if sb is None else tuple(sb)))
+            return 1
+
+        def __getattr__(self, name):
+            return lambda *a: 0
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: type("S", (), {"cuda_stream": 0})())
+    monkeypatch.setattr(runtime, "load_library", lambda *a, **k: Lib())
+    monkeypatch.setattr(runtime.CompiledStencil, "handle", property(lambda self: ctypes.c_void_p(1)))
+    st = testing.load_ir("upwind5_f32", "staged")
+    fields, params, origins, domain = testing.make_case_data(st, "upwind5_f32", domain=(40, 20, 2), seed=0)
+    a = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+    b = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+    fr = B200Stencil(st, {"device_sync": False}).freeze(origin=origins, domain=domain)
+    names = [p["name"] for p in st["params"] if p["t"] == "field"]
+    base = lambda s: [s[n].data_ptr + sum(o * e for o, e in zip((0, 0, 0), s[n].element_strides)) for n in names]  # noqa: E731
+    for s in (a, b, a, b):
+        fr(**s, **params)
+    assert [c[0] for c in seen] == [base(a), base(b), base(a), base(b)] and len(fr._cache) == 2
+    assert seen[0][1] == seen[1][1] and seen[0][2] == domain and seen[0][3] is None
+    p2 = dict(params)
+    first = next(iter(p2))
+    p2[first] = type(p2[first])(0.125)
+    fr(**a, **p2, subbox=(0, 40, 4, 16))
+    assert seen[-1][1] != seen[0][1] and seen[-1][3] == (0, 40, 4, 16)
+    # same objects, one of them re-pointed in place (torch set_): the cached descriptors must not be reused
+    t = {k: v.torch().clone() for k, v in a.items()}
+    monkeypatch.setattr(runtime, "as_view", lambda o: runtime.ArrayView(o.data_ptr(), o.shape, o.stride(), np.dtype("float32"), o)
+                        if isinstance(o, torch.Tensor) else runtime.ArrayView(o.data_ptr, o.shape, o.element_strides, o.dtype, o))  # fmt: skip
+    fr(**t, **params)
+    before = seen[-1][0]
+    t[names[0]].set_(t[names[0]].clone())
+    fr(**t, **params)
+    assert seen[-1][0][0] != before[0] and seen[-1][0][1:] == before[1:]
