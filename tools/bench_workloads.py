@@ -65,6 +65,9 @@ def fused_description(w, steps):
     st = fuse.compose("_".join(dict.fromkeys(s["fixture"] for s in steps)) + f"_fused{len(steps)}",
                       [(s["ir"], s["binding"]) for s in steps], intermediates=w.get("fuse_intermediates", []))  # fmt: skip
     binding = {p["name"]: p["name"] for p in st["params"] if p["t"] == "field"}
+    for fname, fi in st["field_info"].items():  # the fused stencil reads the combined halo: the workload must provide it
+        if fi is not None and any(max(b) > w["halo"][a] for a, b in enumerate(fi["boundary"])):
+            raise SystemExit(f"--fuse: field {fname} needs halo {fi['boundary']}, the workload allocates {w['halo']}")
     return [dict(fixture=st["name"], variant="fused", ir=st, binding=binding, bytes_per_cell=testing.algorithmic_bytes_per_cell(st),
                  params_from=[s["fixture"] for s in steps])]  # fmt: skip
 
