@@ -37,6 +37,7 @@ step 300  ncu_fused  ncu --set full --clock-control none --import-source on -k r
 step 300  cfg3       python tools/bench_workloads.py --workload tridiagonal --steps 20
 step 300  cfg4       python tools/bench_workloads.py --workload upwind5 --steps 20
 step 300  cfg5       python tools/bench_workloads.py --workload fastwaves --steps 10
+step 300  cfg5_fused python tools/bench_workloads.py --workload fastwaves --fuse --steps 10
 step 300  x2         python tools/bench_workloads.py --workload hdiff_x2 --steps 20
 step 300  x2_fused   python tools/bench_workloads.py --workload hdiff_x2 --fuse --steps 20
 step 600  variants   python tools/bench_configs.py
