@@ -248,3 +248,28 @@ def test_frozen_stencil_descriptor_cache(monkeypatch):
     t[names[0]].set_(t[names[0]].clone())
     fr(**t, **params)
     assert seen[-1][0][0] != before[0] and seen[-1][0][1:] == before[1:]
+
+
+def test_launcher_accepts_every_generated_plan():
+    """The C launcher parses the launch plan before it touches CUDA: without a device a well-formed plan must fail
+    with NO_DEVICE (or CUDA), never with INVALID — checked for every fixture x lowering x generator and for fused IRs."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    from gt4py_b200 import codegen, fuse, testing
+
+    lib = runtime.load_library()
+    hd = testing.load_ir("hdiff_f32", "staged")
+    irs = [(testing.load_ir(n, v), o) for n in testing.list_cases() for v in ("default", "staged") for o in ({"strategy": "auto"}, {"strategy": "point"})]
+    irs.append((fuse.repeat(hd, 2, carry=("in_field", "out_field")), {}))
+    irs.append((testing.load_ir("tridiagonal_f64", "default"), {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 110 * 1024}))
+    bad = []
+    for st, opts in irs:
+        _src, plan = codegen.generate(st, opts)
+        h = ctypes.c_void_p()
+        rc = lib.b200_stencil_load(b"\\x7fELF-not-a-real-cubin", 22, codegen.plan_to_text(plan).encode(), ctypes.byref(h))
+        msg = lib.b200_last_error().decode(errors="replace")
+        if rc >= 0 or "plan" in msg:
+            bad.append((st["name"], opts, rc, msg))
+    assert not bad, bad[:3]
