@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N>1: always exchange first, then compute the whole slab")
     ap.add_argument("--step-mode", default=None, choices=["serial", "overlap", "thin"],
                     help="N>1: force one step schedule (default: a short trial of all of them, fastest on the max over ranks wins)")
-    ap.add_argument("--watchdog", type=float, default=420.0, help="abort instead of hanging after this many seconds")
+    ap.add_argument("--watchdog", type=float, default=600.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-autotune", action="store_true", help="use the default code-generation options")
     ap.add_argument("--tune-in-process", action="store_true", help="run the autotune sweep in this process instead of a child")
@@ -328,7 +328,7 @@ def run_b200(args):
             if args.tune_in_process:
                 tuned = stencil.autotune(sets[0], {}, domain=domain, origin=origins, iters=20)
             else:
-                tuned = stencil.autotune_isolated(sets[0], {}, domain=domain, origin=origins, iters=20, timeout=min(240.0, args.watchdog / 2), device=local_rank)
+                tuned = stencil.autotune_isolated(sets[0], {}, domain=domain, origin=origins, iters=20, timeout=min(180.0, args.watchdog / 3), device=local_rank)
         except Exception as exc:  # keep the measured default rather than lose the bench line
             tuned = f"autotune failed, default options used: {type(exc).__name__}: {str(exc)[-400:]}"
     frozen = stencil.freeze(origin=origins, domain=domain)
