@@ -44,6 +44,7 @@ STENCIL, VARIANT = "hdiff_f32", "staged"
 BYTES_PER_CELL = 12
 METRIC = "Mcell-updates/s + achieved HBM GB/s, horiz-diffusion 1024x1024x80 fp32"
 CPU_SAMPLE = (256, 256, 16)
+_PARTIAL_LINE = None  # rank 0: the bench line without e2e, once the device-timed part is done (printed by the watchdog)
 STRIP = 64  # rows of the boundary strips in the overlapped multi-GPU step (reset to the tuned J tile of the kernel)
 
 
@@ -233,6 +234,15 @@ class ClockSampler:
         }
 
 
+def _watchdog_abort(seconds: float):
+    """The run exceeded its time limit: print what was measured so far (rank 0, if the device-timed part is done) and leave."""
+    if _PARTIAL_LINE is not None:
+        print(json.dumps(_PARTIAL_LINE), flush=True)
+    sys.stderr.write(f"bench.py: watchdog fired after {seconds:.0f} s (rank {os.environ.get('RANK', '0')}) - aborting\n")
+    sys.stderr.flush()
+    os._exit(3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,12 +267,7 @@ def main():
     args.step_mode = args.step_mode or ("overlap" if args.overlap else ("serial" if args.no_overlap else "auto"))
 
     # never hang the box: a lost peer / unmatched exchange turns into a loud non-zero exit
-    def _abort():
-        sys.stderr.write(f"bench.py: watchdog fired after {args.watchdog:.0f} s (rank {os.environ.get('RANK', '0')}) - aborting\n")
-        sys.stderr.flush()
-        os._exit(3)
-
-    wd = threading.Timer(args.watchdog, _abort)
+    wd = threading.Timer(args.watchdog, _watchdog_abort, args=(args.watchdog,))
     wd.daemon = True
     wd.start()
     try:
@@ -517,6 +522,58 @@ def run_b200(args):
         except Exception:
             traffic = None
 
+    def make_line(e2e):
+        return {
+            "metric": METRIC,
+            "value": round(value, 1),
+            "unit": "Mcell-updates/s",
+            "n_gpus": n_gpus,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 5),
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"horizontal diffusion (lap-of-lap + flux limiter) {NI}x{NJ}x{NK} fp32 per GPU "
+                f"(BASELINE configs[1]), literal_float_precision=32, fields {shape} origin {origin3}",
+                "parallelism": "single GPU" if n_gpus == 1 else f"J-slab decomposition x{n_gpus}, NCCL halo exchange "
+                + {"serial": "(exchange, then the whole slab)", "overlap": "overlapped with the interior tiles, whole-tile boundary strips behind",
+                   "thin": f"overlapped with the interior, {THIN}-row boundary strips on a high-priority side stream"}[mode["now"]]
+                + (f"; schedule chosen by trial {overlap_trial}" if overlap_trial else ""),
+                "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
+                "strategy": args.strategy,
+                "codegen_options": stencil.backend_options,
+                "autotune": tuned,
+                "autotune_rejected": getattr(stencil, "tune_rejected", None),
+                "kernels": stencil.compiled.kernel_names(),
+            },
+            "gpu_launches": launches,
+            "e2e": e2e,
+            "roofline": {
+                "bound": "hbm",
+                "achieved": round(achieved, 1),
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": round(achieved / peak, 4),
+                "traffic": traffic,
+                "traffic_source": traffic_src,
+                "peak_source": peak_src,
+                "kernel_ms": round(kernel_ms, 5),
+                "algorithmic_bytes_per_launch": NI * NJ * NK * BYTES_PER_CELL,
+            },
+            "clocks": clocks.summary() if clocks is not None else None,
+        }
+
+    global _PARTIAL_LINE
+    if rank == 0:  # what the watchdog prints if a later, optional phase hangs: the device-timed result is not lost
+        _PARTIAL_LINE = make_line({"value": None, "unit": "Mcell-updates/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                   "note": "not measured: the run was aborted by the watchdog during the end-to-end phase"})
+        if cpu_line is not None:
+            _PARTIAL_LINE["cpu_baseline"] = cpu_line
+
     # ---- end-to-end through the public call with host buffers -------------------------------------
     # pinned host mirrors with the SAME pitched layout as the device storages, so every transfer is one
     # contiguous DMA of the padded buffer (not a strided element-wise copy over PCIe)
@@ -597,52 +654,11 @@ def run_b200(args):
         e2e["note"] = pipe_note
 
     if rank == 0:
-        line = {
-            "metric": METRIC,
-            "value": round(value, 1),
-            "unit": "Mcell-updates/s",
-            "n_gpus": n_gpus,
-            "steps": args.steps,
-            "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 5),
-            "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": {
-                "workload": f"horizontal diffusion (lap-of-lap + flux limiter) {NI}x{NJ}x{NK} fp32 per GPU "
-                f"(BASELINE configs[1]), literal_float_precision=32, fields {shape} origin {origin3}",
-                "parallelism": "single GPU" if n_gpus == 1 else f"J-slab decomposition x{n_gpus}, NCCL halo exchange "
-                + {"serial": "(exchange, then the whole slab)", "overlap": "overlapped with the interior tiles, whole-tile boundary strips behind",
-                   "thin": f"overlapped with the interior, {THIN}-row boundary strips on a high-priority side stream"}[mode["now"]]
-                + (f"; schedule chosen by trial {overlap_trial}" if overlap_trial else ""),
-                "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",
-                "strategy": args.strategy,
-                "codegen_options": stencil.backend_options,
-                "autotune": tuned,
-                "autotune_rejected": getattr(stencil, "tune_rejected", None),
-                "kernels": stencil.compiled.kernel_names(),
-            },
-            "gpu_launches": launches,
-            "e2e": e2e,
-            "roofline": {
-                "bound": "hbm",
-                "achieved": round(achieved, 1),
-                "peak": peak,
-                "unit": "GB/s",
-                "frac": round(achieved / peak, 4),
-                "traffic": traffic,
-                "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "kernel_ms": round(kernel_ms, 5),
-                "algorithmic_bytes_per_launch": NI * NJ * NK * BYTES_PER_CELL,
-            },
-            "clocks": clocks.summary() if clocks is not None else None,
-        }
+        line = make_line(e2e)
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
-        print(json.dumps(line))
+        _PARTIAL_LINE = None  # the full line supersedes it (a hang at teardown must not print a second line)
+        print(json.dumps(line), flush=True)
     if exchanger is not None:
         exchanger.close()
     if dist is not None:

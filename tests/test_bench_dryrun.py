@@ -212,3 +212,22 @@ def test_bench_main_dry_run_two_ranks(monkeypatch, capsys, extra):
         assert ((0, 64, 16, 144), None, None) in calls["subboxes"]  # interior: the tuned kernel on the compute stream
     else:
         assert "schedule chosen by trial" in par and set(line["config"]["parallelism"].split("'ms_per_step': ")[1][:80].replace("'", '"').split('"')[1::2]) >= {"serial", "overlap", "thin"}
+
+
+def test_watchdog_prints_the_device_timed_part(monkeypatch, capsys):
+    """a hang in a later, optional phase (end-to-end pipeline) must not lose the device-timed measurement"""
+    import os
+
+    import bench
+
+    monkeypatch.setattr(os, "_exit", lambda code: (_ for _ in ()).throw(SystemExit(code)))
+    monkeypatch.setattr(bench, "_PARTIAL_LINE", {"metric": bench.METRIC, "value": 1.0, "e2e": {"value": None, "note": "not measured"}})
+    with pytest.raises(SystemExit) as exc:
+        bench._watchdog_abort(5)
+    assert exc.value.code == 3
+    out = capsys.readouterr()
+    assert json.loads(out.out.strip())["value"] == 1.0 and "watchdog fired" in out.err
+    monkeypatch.setattr(bench, "_PARTIAL_LINE", None)
+    with pytest.raises(SystemExit):
+        bench._watchdog_abort(5)
+    assert capsys.readouterr().out == ""
