@@ -15,8 +15,7 @@ import ctypes
 
 import numpy as np
 
-SKIP = ("test_capture_before_first_call_fails_loudly", "test_no_cpu_fallback",
-        "test_gt_dims_permutation")  # (__cuda_array_interface__ of a host tensor)
+SKIP = ("test_capture_before_first_call_fails_loudly", "test_no_cpu_fallback")
 
 
 class _Event:
@@ -77,6 +76,13 @@ def install(mp) -> None:
     mp.setattr(torch.Tensor, "pin_memory", lambda self: self)
     mp.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     mp.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
+
+    def cai(self):  # host tensors pose as device arrays for objects that export __cuda_array_interface__ themselves
+        np_dtype = np.dtype(str(self.dtype).replace("torch.", ""))
+        return {"shape": tuple(self.shape), "typestr": np_dtype.str, "data": (self.data_ptr(), False),
+                "strides": tuple(s * np_dtype.itemsize for s in self.stride()), "version": 3}  # fmt: skip
+
+    mp.setattr(torch.Tensor, "__cuda_array_interface__", property(cai))
 
     real_as_view = runtime.as_view
 
