@@ -226,6 +226,8 @@ class DeviceArray:
         torch = _torch()
         if isinstance(value, DeviceArray):
             value = value.torch()
+        elif isinstance(value, np.generic):  # NumPy scalars (gt4py's ones()/full() assign `dtype(1)`): torch wants Python scalars
+            value = value.item()
         elif isinstance(value, np.ndarray):
             value = torch.from_numpy(np.ascontiguousarray(value)).to(self._base.device, non_blocking=False)
         elif hasattr(value, "__cuda_array_interface__") and not isinstance(value, torch.Tensor):

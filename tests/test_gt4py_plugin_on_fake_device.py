@@ -81,3 +81,53 @@ def test_b200_stencils_match_the_numpy_backend_through_the_gt4py_call_path(fake_
     np.testing.assert_array_equal(results["b200"][0], results["numpy"][0])
     np.testing.assert_array_equal(results["b200"][1], results["numpy"][1])
     assert np.abs(results["b200"][0]).sum() > 0 and np.abs(results["b200"][1]).sum() > 0
+
+
+def test_lower_dimensional_data_dim_and_masked_fields_through_the_plugin(fake_device):
+    """IJ-only / K-only fields, a data-dimension field, integer fields with an `if`, storage constructors and host
+    copies of b200 storages — all through gt4py's own interfaces, against the numpy backend"""
+    warnings.filterwarnings("ignore")
+    import gt4py.storage as gt_storage
+    from gt4py.cartesian import gtscript
+    from gt4py.cartesian.gtscript import IJ, PARALLEL, Field, K, computation, interval
+
+    import gt4py_b200  # noqa: F401
+
+    def build(backend):
+        @gtscript.stencil(backend=backend, rebuild=True)
+        def mixed(a: Field[np.float64], sfc: Field[IJ, np.float64], prof: Field[K, np.float64],
+                  vec: Field[(np.float64, (3,))], flag: Field[np.int32], out: Field[np.float64], *, w: np.float64):  # fmt: skip
+            with computation(PARALLEL), interval(...):
+                tmp = a * prof + sfc + vec[0, 0, 0][1] * w
+                if flag > 0:
+                    out = tmp + a[1, 0, 0]
+                else:
+                    out = tmp - a[0, -1, 0]
+
+        return mixed
+
+    rng = np.random.default_rng(9)
+    ni, nj, nk = 18, 11, 5
+    host = {
+        "a": rng.random((ni + 2, nj + 2, nk)), "sfc": rng.random((ni + 2, nj + 2)), "prof": rng.random((nk,)),
+        "vec": rng.random((ni + 2, nj + 2, nk, 3)), "flag": rng.integers(-2, 3, (ni + 2, nj + 2, nk)).astype(np.int32),
+    }  # fmt: skip
+    dims = {"a": "IJK", "sfc": "IJ", "prof": "K", "vec": ["I", "J", "K", "0"], "flag": "IJK"}
+    outs = {}
+    for backend in ("numpy", "b200"):
+        st = build(backend)
+        args = {}
+        for n, h in host.items():
+            d = list(dims[n])
+            ai = tuple(1 if x in "IJ" else 0 for x in d)
+            args[n] = gt_storage.from_array(h, h.dtype, backend=backend, aligned_index=ai, dimensions=d)
+        out = gt_storage.full((ni + 2, nj + 2, nk), -7.0, np.float64, backend=backend, aligned_index=(1, 1, 0))
+        st(**args, out=out, w=np.float64(1.5), origin={"_all_": (1, 1, 0), "prof": (0,), "sfc": (1, 1)}, domain=(ni, nj, nk))
+        outs[backend] = np.asarray(out)  # (__array__ of the b200 storage = device -> host copy)
+        if backend == "b200":
+            ones = gt_storage.ones((4, 5, 6), np.float32, backend="b200", aligned_index=(0, 0, 0))
+            assert np.asarray(ones).sum() == 120 and ones.dtype == np.float32
+            sl = ones[1:3, :, 2]  # slicing keeps a device view
+            assert tuple(sl.shape) == (2, 5)
+    np.testing.assert_array_equal(outs["b200"], outs["numpy"])
+    assert (outs["b200"][1:-1, 1:-1] != -7.0).all() and (outs["b200"][0] == -7.0).all()
