@@ -131,3 +131,42 @@ def test_lower_dimensional_data_dim_and_masked_fields_through_the_plugin(fake_de
             assert tuple(sl.shape) == (2, 5)
     np.testing.assert_array_equal(outs["b200"], outs["numpy"])
     assert (outs["b200"][1:-1, 1:-1] != -7.0).all() and (outs["b200"][0] == -7.0).all()
+
+
+def test_frozen_stencil_backend_options_and_rebuild_from_cache(fake_device):
+    """gt4py's `freeze()`, backend options (`device_sync`, the b200 code-generation options) and a second build of
+    the same definition (served from .gt_cache with the persisted cubin + plan) through the real call path"""
+    warnings.filterwarnings("ignore")
+    import gt4py.storage as gt_storage
+    from gt4py.cartesian import gtscript
+    from gt4py.cartesian.gtscript import PARALLEL, Field, computation, interval
+
+    import gt4py_b200  # noqa: F401
+    from gt4py_b200 import backend as b2backend
+
+    F = Field[np.float32]
+
+    def definition(u: F, c: F, out: F):
+        with computation(PARALLEL), interval(...):
+            lap = 4.0 * u[0, 0, 0] - (u[1, 0, 0] + u[-1, 0, 0] + u[0, 1, 0] + u[0, -1, 0])
+            out = u - c * (lap[1, 0, 0] - lap[-1, 0, 0] + lap[0, 1, 0] - lap[0, -1, 0])
+
+    rng = np.random.default_rng(12)
+    shape, origin, domain = (40, 22, 4), (2, 2, 0), (36, 18, 4)
+    u_h, c_h = rng.random(shape, dtype=np.float32), rng.random(shape, dtype=np.float32)
+    ref = gtscript.stencil(backend="numpy", definition=definition, name="frz", literal_float_precision=32)
+    mk = lambda a, b: gt_storage.from_array(a, np.float32, backend=b, aligned_index=origin)  # noqa: E731
+    o_ref = gt_storage.zeros(shape, np.float32, backend="numpy", aligned_index=origin)
+    ref(mk(u_h, "numpy"), mk(c_h, "numpy"), o_ref, origin=origin, domain=domain)
+    for n, opts in enumerate(({"device_sync": False}, {"device_sync": False, "interior_loop": True, "specialize": "lazy"}, {})):
+        st = gtscript.stencil(backend="b200", definition=definition, name="frz", literal_float_precision=32, rebuild=(n < 2), **opts)
+        assert st.backend == "b200"
+        u, c = mk(u_h, "b200"), mk(c_h, "b200")
+        out = gt_storage.zeros(shape, np.float32, backend="b200", aligned_index=origin)
+        frozen = st.freeze(origin={"u": origin, "c": origin, "out": origin}, domain=domain)
+        frozen(u=u, c=c, out=out)
+        np.testing.assert_array_equal(out.get(), np.asarray(o_ref), err_msg=str(opts))
+        out2 = gt_storage.zeros(shape, np.float32, backend="b200", aligned_index=origin)
+        st(u, c, out2, origin=origin, domain=domain, validate_args=False)
+        np.testing.assert_array_equal(out2.get(), np.asarray(o_ref))
+    assert len(b2backend._COMPILED) >= 1
