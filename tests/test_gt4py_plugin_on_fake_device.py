@@ -170,3 +170,52 @@ def test_frozen_stencil_backend_options_and_rebuild_from_cache(fake_device):
         st(u, c, out2, origin=origin, domain=domain, validate_args=False)
         np.testing.assert_array_equal(out2.get(), np.asarray(o_ref))
     assert len(b2backend._COMPILED) >= 1
+
+
+def test_fusing_and_graphing_gt4py_stencil_objects(fake_device):
+    """two applications of a `backend="b200"` StencilObject as ONE fused stencil (fuse.fuse_stencils) and as one
+    captured graph (StencilGraph) == two calls of the numpy-backend stencil"""
+    warnings.filterwarnings("ignore")
+    import gt4py.storage as gt_storage
+    from gt4py.cartesian import gtscript
+    from gt4py.cartesian.gtscript import PARALLEL, Field, computation, interval
+
+    import gt4py_b200  # noqa: F401
+    from gt4py_b200 import fuse
+    from gt4py_b200.graph import StencilGraph
+
+    F = Field[np.float64]
+
+    def definition(u: F, out: F):
+        with computation(PARALLEL), interval(...):
+            out = 0.5 * u + 0.125 * (u[1, 0, 0] + u[-1, 0, 0] + u[0, 1, 0] + u[0, -1, 0])
+
+    rng = np.random.default_rng(21)
+    shape, dom = (30, 26, 3), (26, 22, 3)
+    u_h = rng.random(shape)
+    ref = gtscript.stencil(backend="numpy", definition=definition, name="avg")
+    mid, out = np.zeros(shape), np.zeros(shape)
+    ref(u_h, mid, origin=(1, 1, 0), domain=(dom[0] + 2, dom[1] + 2, dom[2]))  # step 1 wherever step 2 reads it
+    ref(mid, out, origin=(2, 2, 0), domain=dom)
+
+    st = gtscript.stencil(backend="b200", definition=definition, name="avg", device_sync=False)
+    two = fuse.fuse_stencils("avg_x2", [(st, {"out": "mid"}), (st, {"u": "mid"})], intermediates=["mid"], options={"device_sync": True})
+    assert two.field_info["u"].boundary[:2] == ((2, 2), (2, 2))
+    u = gt_storage.from_array(u_h, backend="b200", aligned_index=(2, 2, 0))
+    o1 = gt_storage.zeros(shape, np.float64, backend="b200", aligned_index=(2, 2, 0))
+    two(u=u, out=o1, origin=(2, 2, 0), domain=dom)
+    np.testing.assert_array_equal(o1.get(), out)
+
+    # the same two steps as a captured sequence of the gt4py object's calls
+    m2 = gt_storage.zeros(shape, np.float64, backend="b200", aligned_index=(2, 2, 0))
+    o2 = gt_storage.zeros(shape, np.float64, backend="b200", aligned_index=(2, 2, 0))
+    st(u, m2, origin=(1, 1, 0), domain=(dom[0] + 2, dom[1] + 2, dom[2]))  # warm-up (also allocates nothing here)
+    m2[...] = 0.0
+    g = StencilGraph()
+    with g:
+        st(u, m2, origin=(1, 1, 0), domain=(dom[0] + 2, dom[1] + 2, dom[2]))
+        st(m2, o2, origin=(2, 2, 0), domain=dom)
+    assert float(np.abs(o2.get()).sum()) == 0.0 and g.num_nodes == 2
+    g.launch()
+    np.testing.assert_array_equal(o2.get(), out)
+    g.close()
