@@ -140,3 +140,33 @@ def test_subbox_launches_compose_to_the_full_domain(name, variant):
             fr(**dev, **params, subbox=box)
         for fname in testing.written_fields(st):
             np.testing.assert_array_equal(dev[fname].get(), ref[fname], err_msg=f"{name}.{variant}/{strategy}:{fname} (I split)")
+
+
+def _smooth_case(ni, nj, nk, seed):
+    """SURVEY §8d second input family: the smooth analytic field of the reference's Burgers demo
+    (5 + 8 (2 + cos(pi (x + 1.5 y)) + sin(2 pi (x + 1.5 y))) / 4) with a constant coefficient 0.025: the flux
+    limiter then sits on exact sign changes and plateaus (products that are exactly zero), not on noise"""
+    st = testing.load_ir("hdiff_f32", "staged")
+    fields, params, origins, domain = testing.make_case_data(st, "hdiff_f32", domain=(ni, nj, nk), seed=seed)
+    shp = fields["in_field"].shape
+    x = np.linspace(0.0, 1.0, shp[0], dtype=np.float64)[:, None, None]
+    y = np.linspace(0.0, 1.0, shp[1], dtype=np.float64)[None, :, None]
+    z = 1.0 + 0.1 * np.arange(shp[2], dtype=np.float64)[None, None, :]
+    fields["in_field"] = (z * (5.0 + 8.0 * (2.0 + np.cos(np.pi * (x + 1.5 * y)) + np.sin(2.0 * np.pi * (x + 1.5 * y))) / 4.0)).astype(np.float32)
+    fields["coeff"] = np.full(fields["coeff"].shape, 0.025, np.float32)
+    return st, fields, params, origins, domain
+
+
+@pytest.mark.parametrize("options", [None, {"strategy": "point"}, {"interior_loop": True, "specialize": "lazy"}])
+def test_hdiff_smooth_analytic_field(options):
+    from gt4py_b200.stencil import B200Stencil
+    from oracle import numpy_oracle
+
+    st, fields, params, origins, domain = _smooth_case(260, 130, 3, seed=1)
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    dev = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+    B200Stencil(st, options)(**dev, origin=origins, domain=domain)
+    np.testing.assert_array_equal(dev["out_field"].get(), ref["out_field"])
+    box = tuple(slice(o, o + d) for o, d in zip(origins["out_field"], domain))
+    assert np.abs(ref["out_field"][box] - ref["in_field"][tuple(slice(o, o + d) for o, d in zip(origins["in_field"], domain))]).max() > 0
