@@ -255,6 +255,162 @@ class DeviceArray:
         out[...] = self
         return out
 
+    # -- ndarray-like arithmetic / comparison / reduction surface -------------------------------------
+    # The reference hands out cupy arrays for GPU backends (storage/cartesian/interface.py), and user code and the
+    # reference's own tests compute with them (`(out[1:-1] == 2).all()`, `field *= 2`, `out.sum()`): the same
+    # expressions work here, evaluated on the device by torch; results are DeviceArrays (C-ordered) or Python scalars.
+    @classmethod
+    def _wrap(cls, t) -> "DeviceArray":
+        torch = _torch()
+        t = t.contiguous()
+        np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+        return cls(t.reshape(-1) if t.numel() else t.reshape(0), 0, tuple(t.shape), tuple(t.stride()) if t.dim() else (), np_dtype)
+
+    @staticmethod
+    def _operand(other):
+        if isinstance(other, DeviceArray):
+            return other.torch()
+        if isinstance(other, np.generic):
+            return other.item()
+        if isinstance(other, np.ndarray):
+            raise TypeError("b200 storage: mixing device storages with host NumPy arrays; copy explicitly (from_array / np.asarray)")
+        return other
+
+    def _binary(self, other, fn, reflected=False):
+        o = self._operand(other)
+        a = self.torch()
+        return self._wrap(fn(o, a) if reflected else fn(a, o))
+
+    def _inplace(self, other, name):
+        getattr(self.torch(), name)(self._operand(other))
+        return self
+
+    def __eq__(self, other):  # noqa: D105  (element-wise, like ndarray; DeviceArray is therefore unhashable)
+        return self._binary(other, lambda a, b: a == b)
+
+    def __ne__(self, other):
+        return self._binary(other, lambda a, b: a != b)
+
+    def __lt__(self, other):
+        return self._binary(other, lambda a, b: a < b)
+
+    def __le__(self, other):
+        return self._binary(other, lambda a, b: a <= b)
+
+    def __gt__(self, other):
+        return self._binary(other, lambda a, b: a > b)
+
+    def __ge__(self, other):
+        return self._binary(other, lambda a, b: a >= b)
+
+    __hash__ = None  # type: ignore[assignment]
+
+    def __add__(self, other):
+        return self._binary(other, lambda a, b: a + b)
+
+    def __radd__(self, other):
+        return self._binary(other, lambda a, b: a + b, reflected=True)
+
+    def __sub__(self, other):
+        return self._binary(other, lambda a, b: a - b)
+
+    def __rsub__(self, other):
+        return self._binary(other, lambda a, b: a - b, reflected=True)
+
+    def __mul__(self, other):
+        return self._binary(other, lambda a, b: a * b)
+
+    def __rmul__(self, other):
+        return self._binary(other, lambda a, b: a * b, reflected=True)
+
+    def __truediv__(self, other):
+        return self._binary(other, lambda a, b: a / b)
+
+    def __rtruediv__(self, other):
+        return self._binary(other, lambda a, b: a / b, reflected=True)
+
+    def __pow__(self, other):
+        return self._binary(other, lambda a, b: a**b)
+
+    def __and__(self, other):
+        return self._binary(other, lambda a, b: a & b)
+
+    def __or__(self, other):
+        return self._binary(other, lambda a, b: a | b)
+
+    def __invert__(self):
+        return self._wrap(~self.torch())
+
+    def __neg__(self):
+        return self._wrap(-self.torch())
+
+    def __abs__(self):
+        return self._wrap(self.torch().abs())
+
+    def __iadd__(self, other):
+        return self._inplace(other, "add_")
+
+    def __isub__(self, other):
+        return self._inplace(other, "sub_")
+
+    def __imul__(self, other):
+        return self._inplace(other, "mul_")
+
+    def __itruediv__(self, other):
+        return self._inplace(other, "div_")
+
+    def _reduce(self, name, axis=None):
+        t = self.torch()
+        if axis is None:
+            return getattr(t, name)().item()
+        return self._wrap(getattr(t, name)(dim=axis) if name in ("sum", "mean", "all", "any") else getattr(t, name)(dim=axis).values)
+
+    def all(self, axis=None):
+        return self._reduce("all", axis)
+
+    def any(self, axis=None):
+        return self._reduce("any", axis)
+
+    def sum(self, axis=None):
+        return self._reduce("sum", axis)
+
+    def mean(self, axis=None):
+        return self._reduce("mean", axis)
+
+    def min(self, axis=None):
+        return self._reduce("min", axis)
+
+    def max(self, axis=None):
+        return self._reduce("max", axis)
+
+    def item(self):
+        if self.size != 1:
+            raise ValueError("can only convert an array of size 1 to a Python scalar")
+        return self.torch().reshape(-1)[0].item()
+
+    def __bool__(self):
+        if self.size != 1:
+            raise ValueError("The truth value of an array with more than one element is ambiguous. Use a.any() or a.all()")
+        return bool(self.item())
+
+    def __float__(self):
+        return float(self.item())
+
+    def __int__(self):
+        return int(self.item())
+
+    def __index__(self):
+        if self.dtype.kind not in "iub":
+            raise TypeError("only integer scalar arrays can be converted to a scalar index")
+        return int(self.item())
+
+    def astype(self, dtype) -> "DeviceArray":
+        return self._wrap(self.torch().to(_torch_dtype(np.dtype(dtype))))
+
+    @property
+    def T(self) -> "DeviceArray":
+        return self.transpose()
+
     def __len__(self):
         return self.shape[0]
 
