@@ -84,3 +84,39 @@ def test_device_array_surface():
     full = storage.full((3, 2, 2), 2.5, np.float64)
     assert float(full.torch().sum()) == 2.5 * 12
     assert storage.is_optimal_layout(b, ("I", "J", "K")) and not storage.is_optimal_layout(t, ("I", "J", "K"))
+
+
+def test_device_array_behaves_like_an_ndarray_in_expressions(monkeypatch):
+    """what user code and the reference's tests do with the cupy arrays of a GPU backend (comparisons, arithmetic,
+    in-place updates, reductions, scalar conversion) on a b200 storage; evaluated by torch on the storage's device
+    (host memory here: the allocator's device is stubbed)"""
+    import torch
+
+    from gt4py_b200 import storage
+
+    monkeypatch.setattr(storage, "_device", lambda device=None: torch.device("cpu"))
+    a_h = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+    a = storage.from_array(a_h, aligned_index=(0, 0, 0))
+    b = storage.full((2, 3, 4), 2.0, np.float64, aligned_index=(0, 0, 0))
+    np.testing.assert_array_equal(((a + b) * 2 - 1).get(), (a_h + 2) * 2 - 1)
+    np.testing.assert_array_equal((1.0 / (a + 1)).get(), 1.0 / (a_h + 1))
+    np.testing.assert_array_equal((-a).get(), -a_h)
+    np.testing.assert_array_equal(abs(a - 10).get(), abs(a_h - 10))
+    assert (b == 2).all() and not (a == 2).all() and (a == 2).any() and (a[1:, :, 2] > 13).all()
+    assert ((a >= 0) & (a < 24)).all() and not (~(a >= 0)).any()
+    assert a.sum() == a_h.sum() and a.max() == 23 and a.min() == 0 and a.mean() == a_h.mean()
+    np.testing.assert_array_equal(a.sum(axis=2).get(), a_h.sum(axis=2))
+    a *= 2
+    a += b
+    a[0] -= 1
+    np.testing.assert_array_equal(a.get(), np.concatenate([a_h[:1] * 2 + 1, a_h[1:] * 2 + 2]))
+    assert float(a[0, 0, 0]) == 1.0 and int(a[1, 2, 3]) == 48 and bool(a[0, 0, 0] == 1) and a[0, 0, 1].item() == 3.0
+    i32 = a.astype(np.int32)
+    assert i32.dtype == np.int32 and i32.get()[1, 2, 3] == 48 and a.T.shape == (4, 3, 2)
+    assert (storage.ones((3,), np.float32, aligned_index=(0,)) * np.float32(3)).dtype == np.float32
+    with pytest.raises(ValueError, match="ambiguous"):
+        bool(a)
+    with pytest.raises(TypeError, match="host NumPy"):
+        a + a_h
+    with pytest.raises(TypeError):
+        hash(a)
