@@ -304,6 +304,7 @@ class DeviceArray:
         return self._binary(other, lambda a, b: a >= b)
 
     __hash__ = None  # type: ignore[assignment]
+    __array_ufunc__ = None  # `np.float64(2) * storage` must reach __rmul__ (device), not silently copy to the host
 
     def __add__(self, other):
         return self._binary(other, lambda a, b: a + b)
@@ -359,29 +360,31 @@ class DeviceArray:
     def __itruediv__(self, other):
         return self._inplace(other, "div_")
 
-    def _reduce(self, name, axis=None):
+    def _reduce(self, name, axis=None, out=None, keepdims=False):
+        if out is not None or keepdims:  # (np.all(x) / np.sum(x) call the method with out=None)
+            raise NotImplementedError("b200 storage: reductions do not support `out` / `keepdims`")
         t = self.torch()
         if axis is None:
             return getattr(t, name)().item()
         return self._wrap(getattr(t, name)(dim=axis) if name in ("sum", "mean", "all", "any") else getattr(t, name)(dim=axis).values)
 
-    def all(self, axis=None):
-        return self._reduce("all", axis)
+    def all(self, axis=None, out=None, keepdims=False):
+        return self._reduce("all", axis, out, keepdims)
 
-    def any(self, axis=None):
-        return self._reduce("any", axis)
+    def any(self, axis=None, out=None, keepdims=False):
+        return self._reduce("any", axis, out, keepdims)
 
-    def sum(self, axis=None):
-        return self._reduce("sum", axis)
+    def sum(self, axis=None, out=None, keepdims=False):
+        return self._reduce("sum", axis, out, keepdims)
 
-    def mean(self, axis=None):
-        return self._reduce("mean", axis)
+    def mean(self, axis=None, out=None, keepdims=False):
+        return self._reduce("mean", axis, out, keepdims)
 
-    def min(self, axis=None):
-        return self._reduce("min", axis)
+    def min(self, axis=None, out=None, keepdims=False):
+        return self._reduce("min", axis, out, keepdims)
 
-    def max(self, axis=None):
-        return self._reduce("max", axis)
+    def max(self, axis=None, out=None, keepdims=False):
+        return self._reduce("max", axis, out, keepdims)
 
     def item(self):
         if self.size != 1:

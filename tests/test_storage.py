@@ -114,6 +114,10 @@ def test_device_array_behaves_like_an_ndarray_in_expressions(monkeypatch):
     i32 = a.astype(np.int32)
     assert i32.dtype == np.int32 and i32.get()[1, 2, 3] == 48 and a.T.shape == (4, 3, 2)
     assert (storage.ones((3,), np.float32, aligned_index=(0,)) * np.float32(3)).dtype == np.float32
+    assert np.all(b == 2) and np.sum(b) == 48.0 and not np.any(b > 2)  # NumPy's reductions dispatch to the methods
+    r = np.float64(2.0) * b  # NumPy scalar on the left: still evaluated on the storage's device
+    assert isinstance(r, storage.DeviceArray) and (r == 4).all()
+    np.testing.assert_array_equal(np.asarray(b), np.full((2, 3, 4), 2.0))
     with pytest.raises(ValueError, match="ambiguous"):
         bool(a)
     with pytest.raises(TypeError, match="host NumPy"):
