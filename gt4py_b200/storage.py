@@ -414,6 +414,17 @@ class DeviceArray:
     def T(self) -> "DeviceArray":
         return self.transpose()
 
+    def reshape(self, *shape) -> "DeviceArray":
+        """A C-ordered array of the new shape (always a copy: the pitched layout has no flat view)."""
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return self._wrap(self.torch().reshape(*shape))
+
+    def flatten(self) -> "DeviceArray":
+        return self.reshape(-1)
+
+    ravel = flatten
+
     def __len__(self):
         return self.shape[0]
 

@@ -111,6 +111,8 @@ def test_device_array_behaves_like_an_ndarray_in_expressions(monkeypatch):
     a[0] -= 1
     np.testing.assert_array_equal(a.get(), np.concatenate([a_h[:1] * 2 + 1, a_h[1:] * 2 + 2]))
     assert float(a[0, 0, 0]) == 1.0 and int(a[1, 2, 3]) == 48 and bool(a[0, 0, 0] == 1) and a[0, 0, 1].item() == 3.0
+    np.testing.assert_array_equal(a.reshape(6, 4).get(), a.get().reshape(6, 4))
+    assert a.flatten().shape == (24,) and [float(x.sum()) for x in a] == [float(x.sum()) for x in a.get()]
     i32 = a.astype(np.int32)
     assert i32.dtype == np.int32 and i32.get()[1, 2, 3] == 48 and a.T.shape == (4, 3, 2)
     assert (storage.ones((3,), np.float32, aligned_index=(0,)) * np.float32(3)).dtype == np.float32
