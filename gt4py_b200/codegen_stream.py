@@ -271,9 +271,12 @@ class StreamKernel:
             for (c, di, dj) in v.reads:
                 if abs(di) > 8:
                     raise NotStreamable("I offset too large")
-        ins = [v for v in self.values if v.kind == "in"]
-        lreach = max([0] + [-v.ni[0] for v in ins])
-        rreach = max([0] + [v.ni[1] for v in ins])
+        # halo lanes: every column at which ANY value is needed must be held by some lane of the warp — inputs read at
+        # an I offset, but also intermediate stages that a later stage reads at an I offset (a stage read at +1 needs a
+        # compute-only lane to the right even when no input is read at a positive offset; found by tools/fuzz_codegen.py)
+        ranged = [v for v in self.values if getattr(v, "ni", None) is not None]
+        lreach = max([0] + [-v.ni[0] for v in ranged])
+        rreach = max([0] + [v.ni[1] for v in ranged])
         self.hl, self.hr = math.ceil(lreach / V), math.ceil(rreach / V)
         self.SQ = 32 - self.hl - self.hr
         self._choose_windows()

@@ -78,7 +78,7 @@ def test_point_generator_on_default_lowering(name):
 
 
 @pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32", "regions_f64",
-                                  "fuse_chain_f32", "fuse_reuse_f64", "fuse_partial_f64"])  # fmt: skip
+                                  "fuse_chain_f32", "fuse_reuse_f64", "fuse_partial_f64", "stage_halo_f32"])  # fmt: skip
 @pytest.mark.parametrize("domain", [(1, 1, 1), (3, 2, 1), (61, 5, 2), (129, 70, 2)])
 def test_ragged_domains_streaming(name, domain):
     run_emulated(name, "staged", {"strategy": "auto"}, domain=domain, seed=2)

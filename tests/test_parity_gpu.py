@@ -25,7 +25,7 @@ def test_fixture_parity_auto_strategy(name):
     run_case(name, "default", {"strategy": "auto"}, seed=1, check_golden=True)
 
 
-@pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32"])
+@pytest.mark.parametrize("name", ["hdiff_f32", "upwind5_f32", "laplacian_f64", "two_stage_par_f32", "fw_pgrad_f32", "stage_halo_f32"])
 @pytest.mark.parametrize("domain", [(1, 1, 1), (3, 2, 1), (127, 5, 2), (129, 33, 3), (260, 70, 4)])
 def test_ragged_domains(name, domain):
     for variant in ("default", "staged"):

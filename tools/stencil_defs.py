@@ -535,6 +535,19 @@ def two_stage_par_f32(a: F32, b: F32, c: F32):
         c = b + t
 
 
+@case("stage_halo_f32", build={"literal_float_precision": 32})
+def stage_halo_f32(a: F32, b: F32, o1: F32, o2: F32):
+    # an intermediate stage read at +1 in I while no INPUT is read at a positive I offset: the streaming kernel needs a
+    # compute-only halo lane on the right (regression of a tools/fuzz_codegen.py finding: halo lanes were derived from
+    # the inputs' reach only, so the last owned column of every warp segment took its own value for the neighbour's)
+    with computation(PARALLEL), interval(...):
+        t0 = a[0, 0, 0]
+        t1 = t0[-1, -1, 0]
+    with computation(PARALLEL), interval(...):
+        o1 = t0[-2, 0, 0] / (abs(a[0, 0, 0]) + 1.0)
+        o2 = b[0, -1, 0] if (t1[1, 2, 0] < t0[0, 0, 0]) else t1[0, 1, 0]
+
+
 # ---------------------------------------------------------------------------------------------
 # Column (FORWARD/BACKWARD) data-flow cases for the register k-cache generator (codegen_column.py)
 # ---------------------------------------------------------------------------------------------
