@@ -15,12 +15,17 @@ literal_float_precision=32.  One "step" = one application of the stencil over th
            MEASURED_PEAKS.json
   N > 1  : weak scaling — the global domain is 1024 x (1024*N) x 80, cut into N J-slabs; every step
            exchanges the two 2-row J-halos of in_field with the neighbour ranks over NCCL (C-ABI
-           b200_halo_exchange) overlapped with the interior of the stencil, then computes the
-           boundary rows.
+           b200_halo_exchange).  Three step schedules (exchange then whole slab / exchange overlapped
+           with the interior + whole-tile boundary strips / + thin strips on a high-priority stream)
+           are checked bit for bit against each other on every rank, timed briefly, and the fastest
+           on the max over ranks is used (`--step-mode` forces one).
+
+The code-generation variant is autotuned in a sacrificial child process (gt4py_b200/tune_worker.py);
+every variant must reproduce the default one bit for bit before it is timed.
 
 `--impl reference` times the CPU restatement of the reference numpy backend (oracle/) on a bounded
-sample of the same workload on the host cores (the reference's GridTools CPU backends cannot be
-built offline: gridtools-cpp headers are not vendored).
+sample of the same workload, one process per usable host core (the reference's GridTools CPU backends
+cannot be built offline: gridtools-cpp headers are not vendored).
 """
 
 from __future__ import annotations
