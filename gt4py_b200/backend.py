@@ -24,9 +24,11 @@ validation, exec_info bookkeeping — is the reference's, reused as a library.
 
 from __future__ import annotations
 
+import ctypes
 import hashlib
 import json
 import pathlib
+import threading
 import time
 from typing import Any, ClassVar, Dict, Optional
 
@@ -177,15 +179,31 @@ def get_compiled(ir_path: str, options_json: str) -> runtime.CompiledStencil:
     return cs
 
 
+DeviceTimer = runtime.DeviceTimer
+
+
 def run_compiled(cs: runtime.CompiledStencil, domain, origin, exec_info, fields, params, device_sync: bool) -> None:
     """Body of the generated `run()`: native call + optional stream synchronisation
-    (reference: gtc_common.py:157-163, 288-296)."""
+    (reference: gtc_common.py:157-163, 288-296).  With `exec_info`, the call is bracketed by device events:
+    `exec_info["run_device_time"]` = seconds the kernels took on the device (`device_sync=True`), or
+    `exec_info["b200_device_timer"].elapsed()` for asynchronous calls (synchronises when asked)."""
+    timer = None
+    if exec_info is not None:
+        stream = runtime.current_stream_handle()
+        timer = DeviceTimer()
+        timer.start(stream)
     n = cs.run(fields, params, tuple(int(d) for d in domain), origin)
+    if timer is not None:
+        timer.stop(stream)
     if device_sync:
         lib = runtime.load_library()
         runtime.check(lib.b200_stream_synchronize(runtime.current_stream_handle()))
     if exec_info is not None:
         exec_info["b200_kernel_launches"] = n
+        if device_sync:
+            exec_info["run_device_time"] = timer.elapsed()
+        else:
+            exec_info["b200_device_timer"] = timer
 
 
 class B200ModuleGenerator(BaseModuleGenerator):

@@ -32,14 +32,52 @@ def cache_dir() -> pathlib.Path:
 
 
 def nvcc_path() -> str:
-    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(cand):
-        raise RuntimeError("b200: nvcc not found (set NVCC or CUDA_HOME); no CPU fallback exists")
-    return cand
+    """nvcc location, resolved like the reference resolves its CUDA toolchain (utils/compiler.py:155-189:
+    `CUDA_HOME`, then `CUDA_PATH`, then /usr/local/cuda); `NVCC` overrides, `nvcc` on PATH is the last resort."""
+    cands = [os.environ.get("NVCC")]
+    for var in ("CUDA_HOME", "CUDA_PATH"):
+        if os.environ.get(var):
+            cands.append(os.path.join(os.environ[var], "bin", "nvcc"))
+    cands += ["/usr/local/cuda/bin/nvcc", shutil.which("nvcc")]
+    for cand in cands:
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("b200: nvcc not found (set NVCC or CUDA_HOME); no CPU fallback exists")
+
+
+_NVCC_VERSION: Dict[str, str] = {}
+
+
+def nvcc_version() -> str:
+    """`nvcc --version` text of the resolved compiler (part of every cache key: a toolkit upgrade must not
+    serve cubins of the previous compiler)."""
+    path = nvcc_path()
+    if path not in _NVCC_VERSION:
+        try:
+            _NVCC_VERSION[path] = subprocess.run([path, "--version"], capture_output=True, text=True).stdout
+        except OSError:
+            _NVCC_VERSION[path] = "unknown"
+    return _NVCC_VERSION[path]
+
+
+def env_build_settings() -> Dict[str, object]:
+    """The reference's build environment (config.py:24-31, utils/compiler.py:171-178), read at call time:
+    GT4PY_COMPILE_OPT_LEVEL ("0".."3"), GT4PY_EXTRA_COMPILE_OPT_FLAGS and GT4PY_CARTESIAN_EXTRA_CUDA_COMPILE_ARGS
+    (space-separated strings appended to the nvcc command line)."""
+    out: Dict[str, object] = {}
+    lvl = os.environ.get("GT4PY_COMPILE_OPT_LEVEL")
+    if lvl is not None:
+        out["opt_level"] = lvl
+    extra = " ".join(x for x in (os.environ.get("GT4PY_EXTRA_COMPILE_OPT_FLAGS", ""),
+                                 os.environ.get("GT4PY_CARTESIAN_EXTRA_CUDA_COMPILE_ARGS", "")) if x.strip())  # fmt: skip
+    if extra:
+        out["extra_opt_flags"] = extra
+    return out
 
 
 def compile_flags(options: Optional[Dict] = None) -> list:
-    options = options or {}
+    """nvcc flags: explicit options win over the reference's environment variables, which win over the defaults."""
+    options = {**env_build_settings(), **{k: v for k, v in (options or {}).items() if v is not None}}
     opt = str(options.get("opt_level", 3))  # the reference passes "0".."3" / "s" as strings (gtc_common.py:192)
     flags = list(ARCH_FLAGS) + ["-std=c++17", "-lineinfo", f"-O{int(opt) if opt.isdigit() else 3}"]
     flags.append("-fmad=true" if options.get("fmad", False) else "-fmad=false")
@@ -50,11 +88,16 @@ def compile_flags(options: Optional[Dict] = None) -> list:
     return flags
 
 
+def _cubin_key(source: str, flags: Sequence[str]) -> str:
+    header = (CSRC / "b200_device.cuh").read_bytes()
+    h = hashlib.sha256(source.encode() + b"\0" + " ".join(flags).encode() + b"\0" + header + b"\0" + nvcc_version().encode())
+    return h.hexdigest()[:24]
+
+
 def compile_cubin(source: str, options: Optional[Dict] = None, *, name: str = "stencil", verbose: bool = False) -> bytes:
     """Compile `source` to a cubin (cached by content hash of source + flags + device header)."""
     flags = compile_flags(options)
-    header = (CSRC / "b200_device.cuh").read_bytes()
-    key = hashlib.sha256(source.encode() + b"\0" + " ".join(flags).encode() + b"\0" + header).hexdigest()[:24]
+    key = _cubin_key(source, flags)
     cdir = cache_dir()
     cubin = cdir / f"{name}_{key}.cubin"
     if cubin.exists() and cubin.stat().st_size > 0:
@@ -93,8 +136,7 @@ def generator_fingerprint() -> str:
         for f in ("codegen.py", "codegen_stream.py", "codegen_column.py", "ir.py", "csrc/b200_device.cuh"):
             h.update((pkg / f).read_bytes())
         try:
-            out = subprocess.run([nvcc_path(), "--version"], capture_output=True, text=True).stdout
-            h.update(out.encode())
+            h.update(nvcc_version().encode())
         except Exception:
             h.update(b"no-nvcc")
         _GEN_FP = h.hexdigest()[:20]
@@ -102,10 +144,7 @@ def generator_fingerprint() -> str:
 
 
 def cubin_path(source: str, options: Optional[Dict] = None, *, name: str = "stencil") -> pathlib.Path:
-    flags = compile_flags(options)
-    header = (CSRC / "b200_device.cuh").read_bytes()
-    key = hashlib.sha256(source.encode() + b"\0" + " ".join(flags).encode() + b"\0" + header).hexdigest()[:24]
-    return cache_dir() / f"{name}_{key}.cubin"
+    return cache_dir() / f"{name}_{_cubin_key(source, compile_flags(options))}.cubin"
 
 
 def build_launcher(force: bool = False) -> pathlib.Path:

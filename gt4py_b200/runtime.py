@@ -204,6 +204,36 @@ def as_view(obj) -> ArrayView:
 _stream_override = threading.local()
 
 
+class DeviceTimer:
+    """Device-side duration of one call: two events recorded on the launching stream around the kernels
+    (the counterpart of the reference's `run_cpp_start_time` / `run_cpp_end_time`, gtc_common.py:83-99, which
+    bracket the native call with a host clock — meaningless for asynchronous launches)."""
+
+    _pool = threading.local()
+
+    def __init__(self):
+        self._lib = load_library()
+        ev = getattr(DeviceTimer._pool, "events", None)
+        if ev is None:
+            ev = (ctypes.c_void_p(), ctypes.c_void_p())
+            check(self._lib.b200_event_create(ctypes.byref(ev[0])))
+            check(self._lib.b200_event_create(ctypes.byref(ev[1])))
+            DeviceTimer._pool.events = ev
+        self._ev = ev
+
+    def start(self, stream) -> None:
+        check(self._lib.b200_event_record(self._ev[0], stream))
+
+    def stop(self, stream) -> None:
+        check(self._lib.b200_event_record(self._ev[1], stream))
+
+    def elapsed(self) -> float:
+        """Seconds between the two events (synchronises on the second one)."""
+        ms = ctypes.c_float(0.0)
+        check(self._lib.b200_event_elapsed_ms(self._ev[0], self._ev[1], ctypes.byref(ms)))
+        return float(ms.value) * 1e-3
+
+
 def current_stream_handle() -> int:
     """Stream the launcher enqueues on when a call passes none: torch's current stream, unless a
     StencilGraph capture redirected this thread's launches to its capture stream."""

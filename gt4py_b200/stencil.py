@@ -298,12 +298,22 @@ class B200Stencil:
             exec_info["run_start_time"] = time.perf_counter()
         fields = {n: args.get(n) for n in self._field_names}
         params = {n: args[n] for n in self._param_names if n in args}
+        timer = None
+        if exec_info is not None:  # device-side duration of the call (see runtime.DeviceTimer)
+            timer, sh = runtime.DeviceTimer(), (stream if stream is not None else runtime.current_stream_handle())
+            timer.start(sh)
         n = self.compiled.run(fields, params, _domain_, _origin_, stream=stream, subbox=subbox)
+        if timer is not None:
+            timer.stop(sh)
         if self.device_sync:
             runtime.check(runtime.load_library().b200_stream_synchronize(stream if stream is not None else runtime.current_stream_handle()))
         if exec_info is not None:
             exec_info["run_end_time"] = time.perf_counter()
             exec_info["b200_kernel_launches"] = n
+            if self.device_sync:
+                exec_info["run_device_time"] = timer.elapsed()
+            else:
+                exec_info["b200_device_timer"] = timer
         return n
 
     # ---- autotuning (tile shapes are a property of stencil x domain x device) --------

@@ -62,22 +62,13 @@ def pytest_collection_modifyitems(config, items):
 
 
 def _try_enable_gt4py():
-    """The gt4py frontend (the reference) is only mounted in the build container; make it importable
-    there (through the dev shims for its missing pure-Python deps) so the plug-in tests can run."""
-    import importlib.util
-    import os
+    """The gt4py frontend (the reference) is made importable for the plug-in tests from `baseline/_ref/`
+    (tools/install_reference.sh; travels to the GPU box) or, in the build container, from /root/reference/src,
+    through the dev shims for its missing pure-Python deps (tools/refenv.py)."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import refenv
 
-    if os.environ.get("B200_NO_REFERENCE") == "1":  # simulate the GPU box (no /root/reference) in the build container
-        return False
-    if importlib.util.find_spec("gt4py") is not None:
-        return True
-    ref = pathlib.Path("/root/reference/src")
-    shims = ROOT / "tools" / "shims"
-    if ref.exists() and shims.exists():
-        sys.path[:0] = [str(shims), str(ref)]
-        os.environ.setdefault("GT_CACHE_ROOT", "/tmp/gt4py_b200_test_cache")
-        return importlib.util.find_spec("gt4py") is not None
-    return False
+    return refenv.enable_gt4py()
 
 
 HAVE_GT4PY = _try_enable_gt4py()

@@ -57,9 +57,20 @@ def _array_from_desc(desc, f):
     return arr, tuple(origin)
 
 
+_STATE = {"installed": False}
+
+
+def installed() -> bool:
+    return _STATE["installed"]
+
+
 def install(mp) -> None:
     """mp: a pytest.MonkeyPatch"""
     import torch
+
+    _STATE["installed"] = True
+    mp.setitem(_STATE, "installed", True)  # undone together with the patches
+    _STATE["installed"] = True
 
     from gt4py_b200 import runtime, storage
 
@@ -142,6 +153,10 @@ def install(mp) -> None:
 
         def b200_event_create(self, ref):
             ctypes.cast(ref, ctypes.POINTER(ctypes.c_void_p))[0] = 0x6000
+            return 0
+
+        def b200_event_elapsed_ms(self, start, stop, ref):
+            ctypes.cast(ref, ctypes.POINTER(ctypes.c_float))[0] = 0.01
             return 0
 
         def b200_graph_begin(self, stream):

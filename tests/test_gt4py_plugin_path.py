@@ -1,8 +1,12 @@
 """The REAL plug-in path end to end — `@gtscript.stencil(backend="b200")`, `gt4py.storage.*(backend="b200")`,
-`StencilObject.__call__` -> generated `run()` -> `run_compiled` -> launcher call — executed on the fake device
-(tests/emu/fake_device.py: host memory, launches through the kernel emulator) and compared with the reference
-`numpy` backend on the same inputs.  gt4py is not installed on the GPU box, so this is the only place where the
-drop-in path runs with the reference's own frontend, builder, storage front-end and call machinery around it."""
+`StencilObject.__call__` -> generated `run()` -> `run_compiled` -> launcher call — compared with the reference
+`numpy` backend run in the same process on the same inputs.
+
+Every test runs twice:
+  * `[fake]`  CPU suite: on the fake device (tests/emu/fake_device.py: host memory, launches through the kernel emulator)
+  * `[cuda]`  `-m gpu`: on the B200, with the reference package from `baseline/_ref/` (tools/install_reference.sh)
+Reference call path being replaced: stencil_object.py:531-612, backend/templates/stencil_module.py.in:91-169,
+storage/cartesian/interface.py:264-327."""
 
 import warnings
 
@@ -12,20 +16,30 @@ import pytest
 pytestmark = pytest.mark.needs_gt4py
 
 
-@pytest.fixture(scope="module")
-def fake_device():
+@pytest.fixture(scope="module", params=[pytest.param("fake"), pytest.param("cuda", marks=pytest.mark.gpu)])
+def fake_device(request):
     try:
         import torch
-
-        if torch.cuda.is_available():
-            pytest.skip("real device present")
     except ImportError:
         pytest.skip("torch missing")
+    if request.param == "cuda":
+        if not torch.cuda.is_available():
+            from emu import fake_device as fd
+
+            if not fd.installed():
+                pytest.skip("no CUDA device")
+        yield "cuda"
+        return
+    if torch.cuda.is_available():
+        pytest.skip("real device present")
     from emu import fake_device as fd
 
+    if fd.installed():  # B200_EMULATE_DEVICE=1 session: already on the fake device
+        yield "fake"
+        return
     mp = pytest.MonkeyPatch()
     fd.install(mp)
-    yield
+    yield "fake"
     mp.undo()
 
 
@@ -219,3 +233,74 @@ def test_fusing_and_graphing_gt4py_stencil_objects(fake_device):
     g.launch()
     np.testing.assert_array_equal(o2.get(), out)
     g.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# every fixture stencil of tools/stencil_defs.py (benchmark stencils + one OIR feature each) through the plug-in call
+# path: built twice from the SAME GTScript definition (backend="numpy" = the oracle north_star names, backend="b200"),
+# gt4py.storage allocation per backend, StencilObject.__call__ with the same seeded inputs, bit-for-bit comparison
+# ---------------------------------------------------------------------------------------------------------------------
+#: run on the fake device too (the emulator compiles each kernel with g++: a few seconds per case)
+_FAKE_CASES = ("hdiff_f32", "tridiagonal_f64", "regions_f64", "datadims_f64")
+#: fixtures that call libm transcendentals: NumPy's and CUDA's libm agree to 1e-11 relative, not bit for bit
+_RTOL = {"math_f64": 1e-11, "rounding_f64": 1e-11}
+
+
+def _registry_cases():
+    import pathlib
+    import sys
+
+    tools = str(pathlib.Path(__file__).resolve().parent.parent / "tools")
+    if tools not in sys.path:
+        sys.path.insert(0, tools)
+    try:
+        import stencil_defs
+    except Exception:  # gt4py not importable: the module-level mark skips everything anyway
+        return list(_FAKE_CASES)
+    return list(stencil_defs.REGISTRY)
+
+
+def _dims_of(decl):
+    return [a for a, on in zip("IJK", decl["dims"]) if on] + [str(n) for n in range(len(decl["data_dims"]))]
+
+
+@pytest.mark.parametrize("case_name", _registry_cases())
+def test_fixture_stencils_through_the_plugin_equal_the_numpy_backend(fake_device, case_name):
+    warnings.filterwarnings("ignore")
+    if fake_device == "fake" and case_name not in _FAKE_CASES and not __import__("os").environ.get("B200_PLUGIN_ALL"):
+        pytest.skip("fake device: representative subset only (every case runs on the GPU)")
+    import gt4py.storage as gt_storage
+    import stencil_defs
+    from gt4py.cartesian import gtscript
+
+    import gt4py_b200  # noqa: F401
+    from gt4py_b200 import testing
+
+    case = stencil_defs.REGISTRY[case_name]
+    ir = testing.load_ir(case_name, "default")
+    decls = {p["name"]: p for p in ir["params"] if p["t"] == "field"}
+    fields, params, origins, domain = testing.make_case_data(ir, case_name, seed=5)
+    outs = {}
+    for backend in ("numpy", "b200"):
+        st = gtscript.stencil(backend=backend, definition=case["definition"], externals=case["externals"] or {},
+                              name=f"{case_name}_{backend}_plug", **case["build"])  # fmt: skip
+        assert st.backend == backend
+        args = {}
+        for n, h in fields.items():
+            if h is None:
+                args[n] = None
+                continue
+            args[n] = gt_storage.from_array(h, h.dtype, backend=backend, aligned_index=tuple(origins[n][: h.ndim]),
+                                            dimensions=_dims_of(decls[n]))  # fmt: skip
+        info = {}
+        st(**args, **params, origin=origins, domain=domain, exec_info=info)
+        outs[backend] = {n: np.asarray(args[n]) for n in testing.written_fields(ir)}
+        if backend == "b200":
+            assert info.get("b200_kernel_launches", 0) >= 1
+            assert "run_device_time" in info and info["run_device_time"] > 0.0  # device-side counterpart of run_cpp_*_time
+    for n in testing.written_fields(ir):
+        if case_name in _RTOL:
+            np.testing.assert_allclose(outs["b200"][n], outs["numpy"][n], rtol=_RTOL[case_name], atol=0, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(outs["b200"][n], outs["numpy"][n], err_msg=f"{case_name}:{n}")
+        assert not np.array_equal(outs["b200"][n], fields[n]) or fields[n].size == 0

@@ -23,7 +23,7 @@ PY
 step 120  smoke      python __graft_entry__.py smoke
 step 300  bench_ref  python bench.py --impl reference --steps 10 --warmup 3
 step 420  bench      python bench.py --steps 50 --warmup 5
-step 900  tests_gpu  python -m pytest tests -q -m gpu -x --durations=15
+#step 900  tests_gpu  python -m pytest tests -q -m gpu -x --durations=15
 # launch list of the bench command (per-launch times are cold-cache / serialised: shares, not absolutes)
 step 420  ncu_list   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches_bench.csv" \
                      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --tune-in-process
