@@ -43,7 +43,7 @@ from gt4py.cartesian.gtc.gtir_to_oir import GTIRToOIR
 from gt4py.cartesian.stencil_object import ArgsInfo, StencilObject, _compute_domain_origin_cache_key
 from gt4py.storage.cartesian import layout as gt_layout, utils as gt_storage_utils
 
-from . import from_oir, ir as b2ir, runtime, storage as b2storage
+from . import from_oir, hostpipe, ir as b2ir, runtime, storage as b2storage
 
 # ---- storage hooks -----------------------------------------------------------------------------
 _orig_allocate_gpu = gt_storage_utils.allocate_gpu
@@ -126,6 +126,13 @@ class B200StencilObject(StencilObject):
             if type(value) in gtscript_frontend._ENUM_REGISTER.values():
                 parameter_args[name] = get_integer_type(lip)(value.value)
 
+        if any(a is not None and hostpipe.is_host_array(a) for a in field_args.values()):
+            # arguments in HOST memory (an extension: the reference's GPU backends refuse them): the stand-alone mirror of
+            # this stencil (same IR, options and cubin) stages them through device storages — hostpipe.host_call
+            self._host_mirror()._call_run(field_args, parameter_args, domain, origin, validate_args=validate_args, exec_info=exec_info)
+            if exec_info is not None:
+                exec_info["call_run_end_time"] = time.perf_counter()
+            return
         array_infos: Dict[str, Optional[ArgsInfo]] = {}
         for name, arg in field_args.items():
             if arg is None:
@@ -156,6 +163,19 @@ class B200StencilObject(StencilObject):
         self.run(_domain_=domain, _origin_=origin, exec_info=exec_info, **views, **parameter_args)
         if exec_info is not None:
             exec_info["call_run_end_time"] = time.perf_counter()
+
+
+    def _host_mirror(self):
+        mirror = type(self).__dict__.get("_b200_host_mirror")
+        if mirror is None:
+            from .stencil import B200Stencil
+
+            g = type(self).run.__globals__  # the generated module: IR file + code-generation options (B200ModuleGenerator)
+            opts = json.loads(g["_B200_OPTS"])
+            mirror = B200Stencil.__new__(B200Stencil)
+            B200Stencil._init_from_compiled(mirror, get_compiled(g["_B200_IR"], g["_B200_OPTS"]), opts)
+            type(self)._b200_host_mirror = mirror
+        return mirror
 
 
 _COMPILED: Dict[str, runtime.CompiledStencil] = {}

@@ -210,7 +210,14 @@ class ExprGen:
         raise CodegenError(f"b200: expression {t}")
 
     # -- statements -----------------------------------------------------------------------------
-    def stmts(self, body, ind: str) -> List[str]:
+    def stmts(self, body, ind: str, masks: Tuple[str, ...] = (), lazy: bool = False) -> List[str]:
+        """Statements of one point.  `masks`: the C conditions of the enclosing `if` / `while` statements.
+
+        Outside a `while` a mask is evaluated once (an `if` block).  INSIDE a `while` (lazy=True) every assignment is
+        guarded by the whole chain, re-evaluated at that statement: the numpy backend — north_star's oracle — inlines
+        the loop condition (AND the enclosing masks) as the `np.where` condition of every statement of the body
+        (gtc/numpy/oir_to_npir.py:149-185, npir_codegen.py:252-267), which differs from a per-point `while` when the
+        loop variable is not updated by the last statement (fixture while_first_f64)."""
         out: List[str] = []
         for s in body:
             t = s["t"]
@@ -218,27 +225,32 @@ class ExprGen:
                 left = s["left"]
                 rhs = self.expr(s["right"])
                 if left["t"] == "scalar":
-                    out.append(f"{ind}{self.locals[left['name']]} = ({CT[left['dtype']]})({rhs});")
+                    line = f"{self.locals[left['name']]} = ({CT[left['dtype']]})({rhs});"
                 else:
                     ct = CT[self.ft.entries[self.ft.index[left['name']]]["dtype"]]
-                    out.append(f"{ind}{self.field_ref(left, for_write=True)} = ({ct})({rhs});")
-            elif t == "mask":
-                out.append(f"{ind}if ({self.expr(s['mask'])}) {{")
-                out += self.stmts(s["body"], ind + "  ")
-                out.append(f"{ind}}}")
+                    line = f"{self.field_ref(left, for_write=True)} = ({ct})({rhs});"
+                out.append(f"{ind}if ({' && '.join(masks)}) {{ {line} }}" if lazy and masks else f"{ind}{line}")
+            elif t in ("mask", "hregion"):
+                if t == "mask":
+                    cond = f"({self.expr(s['mask'])})"
+                else:
+                    conds = []
+                    for var, n_sym, (lo, hi) in ((self.i, f"{self.A}.g.nI", s["i"]), (self.j, f"{self.A}.g.nJ", s["j"])):
+                        if lo is not None:
+                            conds.append(f"{var} >= {_bound(lo, n_sym)}")
+                        if hi is not None:
+                            conds.append(f"{var} < {_bound(hi, n_sym)}")
+                    cond = f"({' && '.join(conds) if conds else 'true'})"
+                if lazy:
+                    out += self.stmts(s["body"], ind, masks + (cond,), True)
+                else:
+                    out.append(f"{ind}if {cond} {{")
+                    out += self.stmts(s["body"], ind + "  ", masks + (cond,), False)
+                    out.append(f"{ind}}}")
             elif t == "while":
-                out.append(f"{ind}while ({self.expr(s['cond'])}) {{")
-                out += self.stmts(s["body"], ind + "  ")
-                out.append(f"{ind}}}")
-            elif t == "hregion":
-                conds = []
-                for var, n_sym, (lo, hi) in ((self.i, f"{self.A}.g.nI", s["i"]), (self.j, f"{self.A}.g.nJ", s["j"])):
-                    if lo is not None:
-                        conds.append(f"{var} >= {_bound(lo, n_sym)}")
-                    if hi is not None:
-                        conds.append(f"{var} < {_bound(hi, n_sym)}")
-                out.append(f"{ind}if ({' && '.join(conds) if conds else 'true'}) {{")
-                out += self.stmts(s["body"], ind + "  ")
+                chain = masks + (f"({self.expr(s['cond'])})",)
+                out.append(f"{ind}while ({' && '.join(chain)}) {{")
+                out += self.stmts(s["body"], ind + "  ", chain, True)
                 out.append(f"{ind}}}")
             else:
                 raise CodegenError(f"b200: statement {t}")
@@ -311,6 +323,27 @@ def _union_extent(hes) -> List[List[int]]:
     return e
 
 
+def _sections_k_coupled(loop) -> bool:
+    """A section of this PARALLEL loop reads, at a K offset (or a variable / absolute K index), a field that ANOTHER
+    section of the loop writes.  The reference merges adjacent-interval PARALLEL loops without a dependency check
+    (gtc/passes/oir_optimizations/vertical_loop_merging.py, AdjacentLoopMerging) and its numpy backend runs the sections
+    one after the other, so `interval(0,2): b = a; interval(2,None): c = b[0,0,-2]` is legal and ordered: the sections
+    must then be separate launches, in order (one kernel with K on blockIdx.z would race across levels)."""
+    secs = loop["sections"]
+    if len(secs) < 2:
+        return False
+    writes, koff_reads = [], []
+    for sec in secs:
+        acc = [a for he in sec["hes"] for a in b2ir.field_accesses(he["body"])]
+        writes.append({a["name"] for a in acc if a["write"]})
+        koff_reads.append({a["name"] for a in acc if not a["write"] and (isinstance(a["off"], dict) or a["off"][2] != 0)})
+    for n, reads in enumerate(koff_reads):
+        for m, w in enumerate(writes):
+            if m != n and reads & w:
+                return True
+    return False
+
+
 def _needs_level_sync(loop) -> bool:
     written, read_off = set(), set()
     for sec in loop["sections"]:
@@ -337,6 +370,7 @@ class Generator:
         self.steps: List[dict] = []
         self.src: List[str] = []
         self.live: set = set()  # fields some kernel addresses in global memory
+        self.tmaps: List[Dict[str, Any]] = []  # tensor maps the launcher encodes into the argument block
 
     # -- argument block ---------------------------------------------------------------------------
     def args_struct(self) -> str:
@@ -352,8 +386,23 @@ class Generator:
             pos = s["offset"] + b2ir.ITEMSIZE[s["dtype"]]
         if size > pos:
             lines.append(f"  char _pad{pad}[{size - pos}];")
+        if self.tmaps:
+            # tensor maps of the bulk-async streaming kernels, encoded by the launcher at every call: 64-byte aligned
+            # right behind the scalars; tmo = {array index of the domain origin along I (incl. the alignment shift of
+            # the map's base), J, K, K multiplier (0 for a field without K axis)} per map
+            lines.append(f"  b200::TMap tm[{len(self.tmaps)}];")
+            lines.append(f"  int tmo[{len(self.tmaps)}][4];")
         lines.append("};")
         return "\n".join(lines)
+
+    def tmap_index(self, field: str, box0: int, box1: int) -> int:
+        """Index (in Args::tm) of the tensor map of `field` with a box of box0 elements x box1 rows."""
+        fi = self.ft.index[field]
+        for n, t in enumerate(self.tmaps):
+            if (t["field"], t["box"]) == (fi, [box0, box1]):
+                return n
+        self.tmaps.append({"field": fi, "box": [box0, box1]})
+        return len(self.tmaps) - 1
 
     # -- kernels ------------------------------------------------------------------------------------
     def _kname(self, tag: str) -> str:
@@ -416,11 +465,12 @@ class Generator:
         return len(self.kernels) - 1
 
     # -- driver -------------------------------------------------------------------------------------
+    # (one kernel for all sections of a PARALLEL loop takes K from blockIdx.z: the sections then run concurrently)
     def lower_loop(self, loop) -> None:
         order = loop["order"]
         if order == "parallel":
             grouped = [(sec["interval"], split_groups(sec["hes"])) for sec in loop["sections"]]
-            if all(len(g) == 1 for _, g in grouped):
+            if all(len(g) == 1 for _, g in grouped) and not _sections_k_coupled(loop):
                 k = self.emit_par_kernel([(iv, g[0]) for iv, g in grouped])
                 self.steps.append({"t": "launch", "kernel": k})
             else:
@@ -489,7 +539,7 @@ class Generator:
         ]
         source = "\n".join(header) + "\n\n".join(self.src) + "\n"
         plan = {
-            "version": 1,
+            "version": 2,
             "name": self.st["name"],
             "fields": [
                 {
@@ -507,6 +557,7 @@ class Generator:
             "scalars_size": scal_size,
             "kernels": self.kernels,
             "steps": self.steps,
+            "tmaps": self.tmaps,
         }
         return source, plan
 
@@ -556,8 +607,11 @@ def plan_to_text(plan: Dict[str, Any]) -> str:
         tile = k.get("tile", [k["block"][0], k["block"][1], 1])
         L.append(
             f"kernel {k['name']} {kind} {k['block'][0]} {k['block'][1]} {k['block'][2]} "
-            f"{tile[0]} {tile[1]} {tile[2]} {e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]} {b(k['k_lo'])} {b(k['k_hi'])} {k['smem']}"
+            f"{tile[0]} {tile[1]} {tile[2]} {e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]} {b(k['k_lo'])} {b(k['k_hi'])} {k['smem']} {int(k.get('qshift', 0))}"
         )
+    L.append(f"ntmaps {len(plan.get('tmaps', []))}")
+    for t in plan.get("tmaps", []):
+        L.append(f"tmap {t['field']} {t['box'][0]} {t['box'][1]}")
     L.append(f"nsteps {len(plan['steps'])}")
     for s in plan["steps"]:
         if s["t"] == "launch":

@@ -166,6 +166,7 @@ class StreamKernel:
                                 if d["kind"] == "api" or name in self.global_fields:
                                     prev = self._in_value(name, 0)
                                     prev.reads.append((stage, 0, 0))
+                                    prev.pass_reads = getattr(prev, "pass_reads", 0) + 1  # only the "else" value of the masked write
                         new = self._new_version(name, stage)
                         self.assign_ver[id(s)] = (new, prev)
                         self.cur[name] = new
@@ -189,6 +190,19 @@ class StreamKernel:
         # drop dead values (never read, never stored)? keep: harmless
         self.written = set(self.cur.keys())
         self._schedule()
+        # in-place update through the stream: a field that this kernel stores may only be READ (in its incoming state)
+        # at the very cells the reading thread owns.  A read at a K offset, or on halo lanes / halo rows (the value
+        # is consumed at an IJ offset, directly or through an intermediate stage computed on an extended extent),
+        # touches cells another warp or tile owns and may already have overwritten: a write-after-read race on the
+        # device, wrong results on any multi-tile domain.  The point generator splits such loops at the hazard.
+        # (Exempt: the incoming value is only the pass-through of ONE masked redefinition, `if m: f = x` — a cell a
+        # neighbour has already stored holds `m ? x : old`, which is what this thread computes from either value.)
+        for v in self.values:
+            if v.kind == "in" and v.field in self.written and (v.dk != 0 or list(v.ni) != [0, 0] or list(v.nj) != [0, 0]):
+                versions = sum(1 for x in self.values if x.kind == "tmp" and x.field == v.field)
+                if v.dk == 0 and versions == 1 and len(v.reads) == getattr(v, "pass_reads", 0):
+                    continue
+                raise NotStreamable(f"field {v.field} is updated in place but read beyond the cells a thread owns")
 
     # ---- lags, windows, needed ranges (pass 2) -----------------------------------------------------
     def _schedule(self) -> None:
@@ -259,7 +273,7 @@ class StreamKernel:
         # register budget: a thread keeps (sum of window rows) x V values live; beyond ~40 32-bit
         # registers of window state the narrower vector (more resident warps) wins (measured on
         # horizontal diffusion: 78.8 % vs 66.6 % of HBM peak, profiles/README.md)
-        pf = int(self.opts.get("prefetch", 1))
+        pf = self._pf()
         rows = sum((v.window + (pf if v.kind == "in" else 0)) * (b2ir.ITEMSIZE[v.dtype] // 4) for v in self.values)
         vmax = self.V
         if self.V == 4 and rows * 4 > 40:
@@ -279,9 +293,21 @@ class StreamKernel:
         rreach = max([0] + [v.ni[1] for v in ranged])
         self.hl, self.hr = math.ceil(lreach / V), math.ceil(rreach / V)
         self.SQ = 32 - self.hl - self.hr
+        # bulk-async variant: a warp row is copied by ONE cp.async.bulk (16-byte aligned source, size a multiple of
+        # 16): when a vector is only 8 bytes (fp32 x 2) the segments must start at even vector indices
+        isz = min(sizes)
+        self.tma_tensor = self.opts.get("tma_mode", "tensor") == "tensor"  # tensor-map copies have no alignment rule for the start
+        self.qalign = 2 if (self.opts.get("tma") and not self.tma_tensor and V * isz == 8) else 1
+        if self.qalign == 2 and self.SQ % 2:
+            self.SQ -= 1
         self._choose_windows()
         self.TJ = int(self.opts.get("tile_j", 64))
         self.NW = int(self.opts.get("warps", 4))
+
+    def _pf(self) -> int:
+        """Extra window rows of the input streams (loads issued that many march steps before first use).  The
+        bulk-async variant (`tma`) needs none: its look-ahead lives in the shared-memory ring, not in registers."""
+        return int(self.opts.get("prefetch", 0 if self.opts.get("tma") else 1))
 
     def _choose_windows(self) -> None:
         """Pick the rotation period U and the final register-window sizes.
@@ -289,7 +315,7 @@ class StreamKernel:
         Inputs get `prefetch` extra rows (loads issued that many march steps before first use ->
         more bytes in flight per warp).  A window that divides U rotates by register renaming in the
         U-times unrolled march loop (no moves); the others shift (W-1 moves per element and step)."""
-        pf = int(self.opts.get("prefetch", 1))
+        pf = self._pf()
         req = {}
         for v in self.values:
             req[id(v)] = v.window + (pf if v.kind == "in" else 0)
@@ -360,7 +386,11 @@ class StreamKernel:
         self.store_ext = [[ei0, ei1], [ej0, ej1]]
         w(f"  const int X0 = {A}.g.i_lo + ({ei0}), X1 = {A}.g.i_hi + ({ei1});")
         w(f"  const int Y0 = {A}.g.j_lo + ({ej0}), Y1 = {A}.g.j_hi + ({ej1});")
-        w("  const int QX0 = (X0 >= 0) ? X0 / V : -((-X0 + V - 1) / V);")
+        w("  const int QXF = (X0 >= 0) ? X0 / V : -((-X0 + V - 1) / V);")
+        if self.qalign == 2:
+            w("  const int QX0 = QXF - (((QXF - HL) % 2 + 2) % 2);   // lane 0 of every segment sits on a 16-byte boundary")
+        else:
+            w("  const int QX0 = QXF;")
         w("  const int nseg = ((X1 - QX0 * V) + SQ * V - 1) / (SQ * V);")
         w("  const int ntj = (Y1 - Y0 + TJ - 1) / TJ;")
         w("  const long long task = (long long)blockIdx.x * NW + threadIdx.y;")
@@ -480,6 +510,78 @@ class StreamKernel:
                     w(f"    q_{v.cname} += {U} * SJ;")
             w("  }")
 
+        def row_at(v, ahead: int, trip_offset: str) -> str:
+            """Address of lane's vector in the row of stream v that march step `t + ahead` loads (outside the trip body)."""
+            c = v.cname
+            if self.SJ and not self._useq:
+                return f"(p_{c} + {trip_offset} + ({ahead - v.lag}) * SJ)"
+            pitch = "SJ" if self.SJ else f"sj_{c}"
+            return f"(q_{c} + {ahead} * {pitch})" if ahead else f"q_{c}"
+
+        def steady_loop_tma(cond):
+            """Bulk-async steady loop: the ring has D slots, a slot holds the input rows of ONE TRIP (U march steps x NS
+            streams); one mbarrier, one wait, one warp sync and one refill (by lane 0) per trip."""
+            D, NS, RB, UT = self.tma, len(ins), self.tma_rb, self.tma_ut
+            slot_bytes = NS * UT * RB
+
+            def issue(slot_expr: str, bar: str, first_step: str, pad: str):
+                w(f"{pad}b200::mbar_expect_tx({bar}, {slot_bytes});")
+                if self.tma_tensor:
+                    # ONE tensor-map copy per stream and trip: a box of 32*V elements x UT rows of level k (+dk), rows
+                    # packed back to back in the slot (coordinates are array indices: domain index + origin)
+                    for n, v in enumerate(ins):
+                        m = gen.tmap_index(v.field, 32 * V, UT)
+                        w(f"{pad}b200::tma_load_3d({slot_expr} + {n * UT * RB}, &A.tm[{m}], g0 + A.tmo[{m}][0], "
+                          f"({first_step} - ({v.lag})) + A.tmo[{m}][1], (k + ({v.dk}) + A.tmo[{m}][2]) * A.tmo[{m}][3], {bar});")
+                    return
+                for n, v in enumerate(ins):
+                    pitch = "SJ" if self.SJ else f"sj_{v.cname}"
+                    w(f"{pad}{{ const {CT[v.dtype]}* src = p_{v.cname} + (long long)({first_step} - ({v.lag})) * {pitch} + g0;")
+                    for u in range(UT):
+                        w(f"{pad}  b200::bulk_g2s({slot_expr} + {(n * UT + u) * RB}, src + {u} * {pitch}, {RB}, {bar});")
+                    w(f"{pad}}}")
+
+            w(f"  if ({cond}) {{   // steady loop (interior, bulk-async ring: {D} slots of {UT} rows x {NS} streams per warp)")
+            w(f"    const int t_tma_end = (t_int > t) ? t + ((t_int - t) / {UT}) * {UT} : t;   // first step after the steady trips")
+            w("    if (t_tma_end > t) {")
+            w(f"      unsigned char* rp = &b200_ring[threadIdx.y][0] + lane * {RB // 32};   // this lane's vector in the current slot")
+            w("      int sl = 0;")
+            w("      unsigned par = 0u;")
+            w("      if (lane == 0) {")
+            w(f"        for (int d = 0; d < {D}; ++d) b200::mbar_init(&b200_bar[threadIdx.y][d], 1);")
+            w("        b200::mbar_fence_init();")
+            for d in range(D):
+                w(f"        if (t + {d * UT} < t_tma_end) {{")
+                issue(f"rp + {d * slot_bytes}", f"&b200_bar[threadIdx.y][{d}]", f"t + {d * UT}", "          ")
+                w("        }")
+            w("      }")
+            w("      __syncwarp();")
+            w(f"      for (; t + {UT} <= t_int; t += {UT}) {{")
+            w("        B200_TRACE(3);")
+            w("        B200_TRACE(5);")
+            if not self._useq:
+                w("        const long long toff = (long long)t * SJ + g0;   // this trip's row offset, shared by all streams")
+            w("        b200::mbar_wait(&b200_bar[threadIdx.y][sl], par);   // the rows of this trip have landed")
+            for u in range(UT):
+                w(f"        {{  // steady step, rotation phase {(ph0 + u) % U}")
+                w(f"          const int tt = t + {u};")
+                L.extend(self._emit_step((ph0 + u) % U, fast="interior", u=u))
+                w("        }")
+            w("        __syncwarp();   // every lane has read the slot: it may be refilled")
+            w(f"        if (lane == 0 && t + {D * UT} < t_tma_end) {{")
+            if self.opts.get("tma_fence", True):
+                w("          b200::fence_async_smem();")
+            issue("rp", "&b200_bar[threadIdx.y][sl]", f"t + {D * UT}", "          ")
+            w("        }")
+            if self.SJ and self._useq:
+                for v in streams:
+                    w(f"        q_{v.cname} += {UT} * SJ;")
+            w(f"        ++sl; rp += {slot_bytes};")
+            w(f"        if (sl == {D}) {{ sl = 0; rp -= {D * slot_bytes}; par ^= 1u; }}")
+            w("      }")
+            w("    }")
+            w("  }")
+
         def prologue(fast):
             # steps until the steady state starts (compile-time count)
             for n in range(n_pro):
@@ -507,10 +609,32 @@ class StreamKernel:
         interior = self.opts.get("interior_loop", False) and self.opts.get("pure_loop", True) and not any(self.row_guard.values())
         # interior_loop="steady": only the steady trips of interior warps are specialised (fewer registers)
         steady_only = interior and self.opts.get("interior_loop") == "steady"
+        # bulk-async variant (option tma=D): the input rows of interior warps come through a per-warp ring of D rows in
+        # shared memory, filled by cp.async.bulk copies that one lane issues D march steps ahead (mbarrier per slot);
+        # the lanes read their vectors with LDS.  Look-ahead costs shared memory instead of registers and L2 prefetches.
+        self.tma = 0
+        ins = [v for v in self.values if v.kind == "in"]
+        if int(self.opts.get("tma", 0) or 0) and interior and ins:
+            isz = b2ir.ITEMSIZE[ins[0].dtype]
+            self.tma_rb = 32 * V * isz  # bytes of one warp row
+            # ring depth in TRIPS; a trip = the smallest multiple of the rotation period with at least `tma_rows` steps.
+            # The ring must fit the shared-memory budget of a CTA (static allocation, and small enough that shared
+            # memory does not cap the resident CTAs below what the registers allow): shorter trips first, then fewer slots.
+            budget = int(self.opts.get("tma_smem_kb", 40)) * 1024
+            want_d = max(2, int(self.opts["tma"]))
+            want_m = max(1, -(-int(self.opts.get("tma_rows", 6)) // U))
+            fits = [(d, m) for d in range(want_d, 1, -1) for m in range(want_m, 0, -1)
+                    if self.NW * d * (len(ins) * m * U * self.tma_rb + 8) <= min(budget, 48 * 1024)]
+            if fits:
+                D, m = fits[0]
+                self.tma, self.tma_ut = D, m * U
+                slot = len(ins) * self.tma_ut * self.tma_rb
+                w(f"  __shared__ __align__(128) unsigned char b200_ring[NW][{D * slot}];   // [warp][slot][stream][step of the trip][row bytes]")
+                w(f"  __shared__ __align__(8) unsigned long long b200_bar[NW][{D}];")
         if interior:
             w("  const bool winterior = __all_sync(0xffffffffu, " + " && ".join(
                 f"full_{v.cname}" if v.kind == "in" else f"(!own || full_{v.cname})" for v in streams) + ");")
-            lim = [f"T_hi + ({b})"] + ([f"pfe_{v.cname}" for v in self.values if v.kind == "in"] if pfd > 0 else [])
+            lim = [f"T_hi + ({b})"] + ([f"pfe_{v.cname}" for v in self.values if v.kind == "in"] if pfd > 0 and not self.tma else [])
             w("  int t_int = " + lim[0] + ";")
             for x in lim[1:]:
                 w(f"  t_int = t_int < {x} ? t_int : {x};")
@@ -520,7 +644,10 @@ class StreamKernel:
             w(f"  if (allvec && wpure && winterior{pitch_ok}) {{")
             prologue("igeneral")
             running_pointers()
-            steady_loop("interior", "true", "t_int")
+            if self.tma:
+                steady_loop_tma("true")
+            else:
+                steady_loop("interior", "true", "t_int")
             tail("igeneral")
             w("  } else {")
         prologue(False)
@@ -535,7 +662,10 @@ class StreamKernel:
         if self.opts.get("edge_loop", False) and self.opts.get("pure_loop", True):
             modes.append(("fast", "allvec && !wpure" + pitch_ok, f"T_hi + ({b})"))
         for mode, cond, bound in modes:
-            steady_loop(mode, cond, bound)
+            if mode == "interior" and self.tma:
+                steady_loop_tma(cond)
+            else:
+                steady_loop(mode, cond, bound)
         tail(False)
         if interior and not steady_only:
             w("  }")
@@ -546,7 +676,7 @@ class StreamKernel:
             {
                 "name": name, "kind": "stream", "block": [32, self.NW, 1], "tile": [self.SQ * V, self.TJ, V],
                 "extent": self.store_ext, "k_lo": self.interval[0], "k_hi": self.interval[1], "smem": 0,
-                "vector": V, "period": U, "windows": {v.cname: (v.window, "shift" if v.shift else "rot") for v in self.values},
+                "qshift": self.qalign - 1, "tma": self.tma, "tma_mode": ("tensor" if self.tma_tensor else "bulk") if self.tma else None, "vector": V, "period": U, "windows": {v.cname: (v.window, "shift" if v.shift else "rot") for v in self.values},
             }
         )  # fmt: skip
         return len(gen.kernels) - 1
@@ -563,8 +693,10 @@ class StreamKernel:
                 for s in range(v.window - 1, 0, -1):
                     L.append(ind + " ".join(f"{self.reg(v, s, e)} = {self.reg(v, s - 1, e)};" for e in range(V)))
         # 1. loads of the newest row of every input stream
+        if fast == "interior" and getattr(self, "tma", 0):
+            L.extend(self._emit_ring_loads(phase, u))
         for v in self.values:
-            if v.kind != "in":
+            if v.kind != "in" or (fast == "interior" and getattr(self, "tma", 0)):
                 continue
             slot = self._new_slot(v, phase)
             c = v.cname
@@ -642,6 +774,21 @@ class StreamKernel:
         # 2. stages
         for si, he in enumerate(self.hes):
             L.extend(self._emit_stage(si, he, phase, fast))
+        return L
+
+    def _emit_ring_loads(self, phase: int, u: int) -> List[str]:
+        """Interior steady step of the bulk-async variant: this lane's vector of every input row of step `u` of the
+        trip, read from the trip's slot in shared memory (the slot's mbarrier was waited for at the top of the trip)."""
+        V, RB = self.V, self.tma_rb
+        ins = [v for v in self.values if v.kind == "in"]
+        ind = "      "
+        L = []
+        for n, v in enumerate(ins):
+            regs = [self.reg(v, self._new_slot(v, phase), e) for e in range(V)]
+            L.append(f"{ind}{_vec_load(CT[v.dtype], V, regs, f'(rp + {(n * self.tma_ut + u) * RB})', ro=False)}")
+        if not self.SJ:
+            for v in ins:
+                L.append(f"{ind}q_{v.cname} += sj_{v.cname};")
         return L
 
     def _row_addr(self, c: str, ahead: int = 0) -> str:
@@ -883,7 +1030,13 @@ def _can_fuse(a, b, stencil) -> bool:
     the stencil accepts (start+x <= end+y for all bounds, guaranteed by domain_info.min_k)."""
     wa, ra_off, _ = _loop_accesses(a)
     wb, _, rb_koff = _loop_accesses(b)
-    if wa & rb_koff or wb & ra_off:
+    # a zero-offset read inside a horizontal execution that runs on an extended extent is a cross-thread read too
+    ra_ext = {
+        acc["name"]
+        for sec in a["sections"] for he in sec["hes"] if any(x != 0 for ax in he["extent"] for x in ax)
+        for acc in b2ir.field_accesses(he["body"]) if not acc["write"]
+    }  # fmt: skip
+    if wa & rb_koff or wb & (ra_off | ra_ext):
         return False
     bounds = [bd for lp in (a, b) for sec in lp["sections"] for bd in sec["interval"]]
     starts = [bd[1] for bd in bounds if bd[0] == "start"]

@@ -66,6 +66,109 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
+// ---- bulk-async (TMA engine) row copies global -> shared, completion on an mbarrier ---------------
+// Used by the `tma` variant of the streaming kernels (codegen_stream.py): one elected lane per warp issues
+// `cp.async.bulk` copies of whole warp rows into a per-warp ring in shared memory D march steps ahead; the
+// lanes wait on the slot's mbarrier and read their vectors with LDS.  SASS: UBLKCP.S.G + SYNCS.
+// A 64-bit word in shared memory per barrier.  `mbar_wait` traps instead of hanging if a phase never completes
+// (protocol error): a hung box would cost the GPU session, a trap is a loud launch failure.
+#ifndef B200_HOST_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// src, dst 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// One (field, box) tensor map of a kernel: 128 opaque bytes encoded by the launcher (cuTensorMapEncodeTiled) into the
+// kernel's argument block.  tma_load_3d copies the box whose first element is (c0, c1, c2) in ARRAY index space
+// into shared memory (rows packed back to back; elements outside the array read as zero).  SASS: UTMALDG.3D.
+struct alignas(64) TMap {
+  unsigned char b[128];
+};
+__device__ __forceinline__ void tma_load_3d(void* dst, const TMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint: at most ~20 us asleep per try
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  for (int spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1 << 15)) __trap();  // ~0.5 s of failed tries: a protocol error, not a slow copy
+}
+#else
+// CPU emulation (tests/emu): copies complete at issue; a barrier word counts completed phases (low half) and
+// pending transaction bytes (high half), so a wait on the wrong parity / an overrun producer aborts the test.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  if ((*bar >> 32) != 0) emu::fail("mbarrier: expect_tx on a barrier with a phase still in flight");
+  *bar += (unsigned long long)bytes << 32;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  if (((uintptr_t)dst & 15) || ((uintptr_t)src & 15) || (bytes & 15) || bytes == 0) emu::fail("cp.async.bulk: misaligned address or size");
+  if ((*bar >> 32) < bytes) emu::fail("cp.async.bulk: more bytes than the barrier expects");
+  memcpy(dst, src, bytes);
+  *bar -= (unsigned long long)bytes << 32;
+  if ((*bar >> 32) == 0) *bar += 1;  // phase complete
+}
+// emulated tensor map (filled by tests/emu/emu.py the way launcher.cu fills the real one)
+struct alignas(64) TMap {
+  union {
+    unsigned char b[128];
+    struct {
+      char* base;
+      long long dim[3], stride[3];  // extents in elements, strides in bytes (stride[0] = element size)
+      int box[2], isz;
+    } e;
+  };
+};
+__device__ __forceinline__ void tma_load_3d(void* dst, const TMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+  const auto& m = tm->e;
+  if (!m.base) emu::fail("tensor map was not encoded");
+  if (((uintptr_t)dst & 127) || ((uintptr_t)m.base & 15) || (m.stride[1] & 15) || (m.stride[2] & 15))
+    emu::fail("cp.async.bulk.tensor: misaligned shared destination, global base or stride");
+  const unsigned bytes = (unsigned)(m.box[0] * m.box[1] * m.isz);
+  if ((*bar >> 32) < bytes) emu::fail("cp.async.bulk.tensor: more bytes than the barrier expects");
+  char* out = (char*)dst;
+  for (int r = 0; r < m.box[1]; ++r)
+    for (int x = 0; x < m.box[0]; ++x, out += m.isz) {
+      const long long i = c0 + x, j = c1 + r, k = c2;
+      if (i < 0 || i >= m.dim[0] || j < 0 || j >= m.dim[1] || k < 0 || k >= m.dim[2]) memset(out, 0, m.isz);
+      else memcpy(out, m.base + i * m.isz + j * m.stride[1] + k * m.stride[2], m.isz);
+    }
+  *bar -= (unsigned long long)bytes << 32;
+  if ((*bar >> 32) == 0) *bar += 1;  // phase complete
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  __syncwarp();  // the issuing lane has run everything it issued before this point
+  const unsigned long long v = *bar;
+  if ((v >> 32) != 0) emu::fail("mbarrier: wait would hang (transaction bytes outstanding)");
+  const unsigned phases = (unsigned)v;
+  if (phases == 0 || ((phases - 1) & 1) != parity) emu::fail("mbarrier: wait on the wrong phase parity (hang or overrun on the device)");
+  __syncwarp();
+}
+#endif
+
 __device__ __forceinline__ int clampk(long long k, int lo, int hi) {
   return (int)(k < lo ? lo : (k > hi - 1 ? hi - 1 : k));
 }

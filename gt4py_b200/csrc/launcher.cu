@@ -17,6 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cuda.h>
+#include <array>
+#include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -78,7 +82,15 @@ struct KernelPlan {
   int ei0, ei1, ej0, ej1;
   Bound k_lo, k_hi;
   int smem;
+  int qshift = 0;  // streaming kernels: segments may start up to this many vectors left of the first stored column
   cudaKernel_t fn = nullptr;
+};
+struct TmapPlan {
+  int field, box0, box1;
+  // last encoded map (re-encoding costs ~1 us per map; calls usually repeat the same buffers)
+  const void* key_base = nullptr;
+  long long key[6] = {0, 0, 0, 0, 0, 0};
+  alignas(64) unsigned char map[128];
 };
 struct SectionPlan {
   Bound k0, k1;
@@ -100,11 +112,21 @@ struct b200_stencil {
   size_t scalars_size = 0;
   std::vector<KernelPlan> kernels;
   std::vector<StepPlan> steps;
+  std::vector<TmapPlan> tmaps;
   cudaLibrary_t lib = nullptr;
   std::vector<char> image;
-  // scratch for temporaries (grow-only, keyed by the domain of the last call)
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
+  // Scratch for temporaries: one grow-only buffer PER STREAM the stencil is launched on, so that calls of the same
+  // stencil on different streams (interior / boundary sub-boxes overlapped with a halo exchange, device_sync=False)
+  // never share temporaries.  A buffer whose address is baked into a captured CUDA graph is never freed before
+  // the stencil is unloaded (it is retired when a later call needs a bigger one).
+  struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool captured = false;
+  };
+  std::map<cudaStream_t, Scratch> scratch;
+  std::vector<void*> retired;
+  std::mutex mu;
   int device = -1;
 };
 
@@ -122,9 +144,9 @@ int parse_plan(const char* text, b200_stencil* st) {
   std::istringstream in(text);
   std::string tok;
   int version = 0;
-  if (!(in >> tok >> version) || tok != "b200plan" || version != 1)
+  if (!(in >> tok >> version) || tok != "b200plan" || version != 2)
     return fail(B200_ERR_INVALID, "launch plan: bad header");
-  int nfields = 0, nkernels = 0, nsteps = 0;
+  int nfields = 0, nkernels = 0, nsteps = 0, ntmaps = 0;
   while (in >> tok) {
     if (tok == "name") {
       in >> st->name;
@@ -142,8 +164,14 @@ int parse_plan(const char* text, b200_stencil* st) {
     } else if (tok == "kernel") {
       KernelPlan k;
       in >> k.name >> k.kind >> k.block[0] >> k.block[1] >> k.block[2] >> k.tile[0] >> k.tile[1] >> k.tile[2] >>
-          k.ei0 >> k.ei1 >> k.ej0 >> k.ej1 >> k.k_lo.level >> k.k_lo.off >> k.k_hi.level >> k.k_hi.off >> k.smem;
+          k.ei0 >> k.ei1 >> k.ej0 >> k.ej1 >> k.k_lo.level >> k.k_lo.off >> k.k_hi.level >> k.k_hi.off >> k.smem >> k.qshift;
       st->kernels.push_back(k);
+    } else if (tok == "ntmaps") {
+      in >> ntmaps;
+    } else if (tok == "tmap") {
+      TmapPlan t;
+      in >> t.field >> t.box0 >> t.box1;
+      st->tmaps.push_back(t);
     } else if (tok == "nsteps") {
       in >> nsteps;
     } else if (tok == "step") {
@@ -178,8 +206,11 @@ int parse_plan(const char* text, b200_stencil* st) {
     }
   }
   if (!in || (int)st->fields.size() != nfields || (int)st->kernels.size() != nkernels ||
-      (int)st->steps.size() != nsteps)
+      (int)st->steps.size() != nsteps || (int)st->tmaps.size() != ntmaps)
     return fail(B200_ERR_INVALID, "launch plan: truncated or inconsistent");
+  for (auto& t : st->tmaps)
+    if (t.field < 0 || t.field >= nfields || t.box0 <= 0 || t.box0 > 256 || t.box1 <= 0 || t.box1 > 256)
+      return fail(B200_ERR_INVALID, "plan: tensor map");
   for (auto& f : st->fields)
     if (!f.is_temp) st->n_api++;
   for (auto& s : st->steps) {
@@ -236,6 +267,63 @@ int vec_ok(const FieldArg& a, int itemsize) {
   return 1;
 }
 
+// cuTensorMapEncodeTiled, resolved at run time (the launcher links the CUDA runtime only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// Tensor map of one field for the bulk-async streaming kernels: a 3-D tensor (I, J, K) over the WHOLE array the caller
+// passed (halo included), box = box0 elements x box1 rows x 1 level.  `start` = address of array element [0,0,0]; the
+// map's base is `start` rounded down to 16 bytes (always inside the same allocation: device allocations are at least
+// 256-byte aligned), the skipped elements are added to the I extent and to the I origin the kernel adds to its
+// coordinates.  tmo = {origin I (+ shift), origin J, origin K, K multiplier}.
+int encode_tmap(TmapPlan& t, const char* start, const int shape[3], const long long s[7], const int origin[3], int itemsize,
+                bool has_k, unsigned char* out_map, int tmo[4]) {
+  const uintptr_t a = (uintptr_t)start;
+  const char* base = start - (a & 15);
+  const int extra = (int)((a & 15) / itemsize);
+  const long long dimk = has_k ? shape[2] : 1;
+  const long long sj = s[1] * itemsize, sk = has_k ? s[2] * itemsize : s[1] * itemsize * shape[1];
+  tmo[0] = origin[0] + extra;
+  tmo[1] = origin[1];
+  tmo[2] = has_k ? origin[2] : 0;
+  tmo[3] = has_k ? 1 : 0;
+  const long long key[6] = {shape[0] + extra, shape[1], dimk, sj, sk, itemsize};
+  if (t.key_base == base && memcmp(t.key, key, sizeof(key)) == 0) {
+    memcpy(out_map, t.map, 128);
+    return B200_OK;
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  CUtensorMap m;
+  const cuuint64_t dims[3] = {(cuuint64_t)key[0], (cuuint64_t)key[1], (cuuint64_t)key[2]};
+  const cuuint64_t strides[2] = {(cuuint64_t)sj, (cuuint64_t)sk};
+  const cuuint32_t box[3] = {(cuuint32_t)t.box0, (cuuint32_t)t.box1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapDataType dt = itemsize == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  CUresult r = enc(&m, dt, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %lld x %lld x %lld, strides %lld / %lld bytes", (int)r,
+                key[0], key[1], key[2], sj, sk);
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(t.map, &m, 128);
+  t.key_base = base;
+  memcpy(t.key, key, sizeof(key));
+  memcpy(out_map, t.map, 128);
+  return B200_OK;
+}
+
 int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, int k_hi, cudaStream_t stream) {
   Geom* g = reinterpret_cast<Geom*>(blob.data());
   int nx = (g->i_hi + k.ei1) - (g->i_lo + k.ei0);
@@ -253,7 +341,9 @@ int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, i
     const int V = k.tile[2];
     const int x0 = g->i_lo + k.ei0, x1 = g->i_hi + k.ei1;
     const int qx0 = x0 >= 0 ? x0 / V : -((-x0 + V - 1) / V);
-    const long long nseg = ((x1 - qx0 * V) + k.tile[0] - 1) / k.tile[0];
+    // qshift > 0 (bulk-async variant: segments start on 16-byte boundaries): the kernel may shift its segment grid
+    // left by up to qshift vectors; size the grid for the worst case, surplus warps leave at once
+    const long long nseg = ((x1 - (qx0 - k.qshift) * V) + k.tile[0] - 1) / k.tile[0];
     const long long ntj = (ny + k.tile[1] - 1) / k.tile[1];
     const long long tasks = nseg * ntj * nz;
     grid = dim3((unsigned)((tasks + k.block[1] - 1) / k.block[1]), 1, 1);
@@ -322,7 +412,11 @@ int b200_stencil_load(const void* image, size_t image_size, const char* plan_tex
 
 int b200_stencil_unload(b200_stencil_t* st) {
   if (!st) return B200_OK;
-  if (st->scratch) cudaFree(st->scratch);
+  // kernels of this stencil may still be in flight (device_sync=False): wait before the code and scratch go away
+  cudaDeviceSynchronize();
+  for (auto& kv : st->scratch)
+    if (kv.second.p) cudaFree(kv.second.p);
+  for (void* p : st->retired) cudaFree(p);
   if (st->lib) cudaLibraryUnload(st->lib);
   delete st;
   return B200_OK;
@@ -357,27 +451,39 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       tl[n] = temp_layout(st->fields[n], domain, need);
       need += tl[n].bytes;
     }
-  if (need > st->scratch_bytes) {
+  char* scratch_base = nullptr;
+  if (need > 0) {
+    std::lock_guard<std::mutex> lock(st->mu);
+    b200_stencil::Scratch& sc = st->scratch[stream];
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     CU(cudaStreamIsCapturing(stream, &cap));
-    if (cap != cudaStreamCaptureStatusNone)
-      return fail(B200_ERR_INVALID,
-                  "stencil %s needs %zu bytes of scratch but the stream is being captured: call it once "
-                  "with this domain before capturing", st->name.c_str(), need);
-    if (st->scratch) {
-      CU(cudaStreamSynchronize(stream));
-      CU(cudaFree(st->scratch));
-      st->scratch = nullptr;
-      st->scratch_bytes = 0;
+    if (need > sc.bytes) {
+      const bool capturing = cap != cudaStreamCaptureStatusNone;
+      if (sc.p) {
+        if (sc.captured || capturing) {
+          st->retired.push_back(sc.p);  // a captured graph launches kernels that point into it: freed at unload
+        } else {
+          CU(cudaStreamSynchronize(stream));
+          CU(cudaFree(sc.p));
+        }
+        sc = b200_stencil::Scratch();
+      }
+      // (legal while capturing: b200_graph_begin captures in relaxed mode, and nothing is freed or synchronised here)
+      CU(cudaMalloc(&sc.p, need));
+      sc.bytes = need;
     }
-    CU(cudaMalloc(&st->scratch, need));
-    st->scratch_bytes = need;
+    if (cap != cudaStreamCaptureStatusNone) sc.captured = true;
+    scratch_base = (char*)sc.p;
   }
 
   // -- argument block --------------------------------------------------------------------------
   const size_t nslots = nf ? nf : 1;
   const size_t scal_off = sizeof(Geom) + sizeof(FieldArg) * nslots;
-  std::vector<char> blob(align_up(scal_off + st->scalars_size, 8), 0);
+  const size_t ntm = st->tmaps.size();
+  const size_t tm_off = align_up(scal_off + st->scalars_size, 64);  // Args::tm (alignas(64)), then Args::tmo
+  std::vector<char> blob(ntm ? align_up(tm_off + ntm * (128 + 16), 64) : align_up(scal_off + st->scalars_size, 8), 0);
+  std::vector<const char*> arr_start(nf, nullptr);  // per field: array element [0,0,0], extents, origin (for the tensor maps)
+  std::vector<std::array<int, 6>> arr_geo(nf);
   Geom* g = reinterpret_cast<Geom*>(blob.data());
   g->nI = domain[0];
   g->nJ = domain[1];
@@ -399,10 +505,13 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       const TempLayout& t = tl[n];
       for (int d = 0; d < 7; ++d) a.s[d] = t.s[d];
       long long off = (long long)t.origin[0] * t.s[0] + (long long)t.origin[1] * t.s[1];
-      a.p = (char*)st->scratch + t.offset + off * fp.itemsize;
+      a.p = scratch_base + t.offset + off * fp.itemsize;
       a.klo = 0;
       a.khi = t.shape[2];
       a.vec = vec_ok(a, fp.itemsize);
+      arr_start[n] = scratch_base + t.offset;
+      // (every element of a row of the scratch layout exists: the I extent of the map is the row pitch)
+      arr_geo[n] = {fp.dims[1] ? (int)t.s[1] : t.shape[0], t.shape[1], t.shape[2], t.origin[0], t.origin[1], t.origin[2]};
     } else {
       const b200_field_t& f = fields[api++];
       if (!f.data) {  // unreferenced argument (AccessKind.NONE)
@@ -417,9 +526,26 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
       a.klo = fp.dims[2] ? -f.origin[2] : 0;
       a.khi = fp.dims[2] ? f.shape[2] - f.origin[2] : 1;
       a.vec = vec_ok(a, fp.itemsize);
+      arr_start[n] = (const char*)f.data;
+      arr_geo[n] = {f.shape[0], f.shape[1], f.shape[2], f.origin[0], f.origin[1], f.origin[2]};
     }
   }
   if (st->scalars_size) memcpy(blob.data() + scal_off, scalars, st->scalars_size);
+  if (ntm) {
+    std::lock_guard<std::mutex> lock(st->mu);  // the per-map encode cache
+    for (size_t m = 0; m < ntm; ++m) {
+      TmapPlan& t = st->tmaps[m];
+      const FieldPlan& fp = st->fields[t.field];
+      const FieldArg& a = fa[t.field];
+      // a field off the vector path never reaches the bulk-async loop (the kernels test FieldArg::vec): map left zeroed
+      if (!a.p || !a.vec || !fp.dims[0] || !fp.dims[1]) continue;
+      const int shape[3] = {arr_geo[t.field][0], arr_geo[t.field][1], arr_geo[t.field][2]};
+      const int origin[3] = {arr_geo[t.field][3], arr_geo[t.field][4], arr_geo[t.field][5]};
+      int rc = encode_tmap(t, arr_start[t.field], shape, a.s, origin, fp.itemsize, fp.dims[2] != 0,
+                           (unsigned char*)blob.data() + tm_off + 128 * m, reinterpret_cast<int*>(blob.data() + tm_off + 128 * ntm) + 4 * m);
+      if (rc < 0) return rc;
+    }
+  }
 
   // -- steps -------------------------------------------------------------------------------------
   int launches = 0;
@@ -611,6 +737,39 @@ int nccl_load() {
     if (r_ != 0) return fail(B200_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));   \
   } while (0)
 
+// Re-layout of a 3-D array between two stride sets (storage.from_array: C-ordered upload -> pitched I-unit-stride
+// storage).  When the unit-stride axes differ the copy goes through a 32 x 32 shared-memory tile so that both the
+// reads and the writes are coalesced (a plain element-wise strided copy reaches ~0.4 TB/s, profiles/r01_launches_bench.csv).
+struct RelayoutArgs {
+  int n[3];
+  long long ds[3], ss[3];
+  int a, b, c, d;
+};
+
+template <class T>
+__global__ void relayout_rows(T* __restrict__ dst, const T* __restrict__ src, RelayoutArgs r) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= r.n[r.a]) return;
+  const long long y = blockIdx.y, z = blockIdx.z;
+  dst[x * r.ds[r.a] + y * r.ds[r.c] + z * r.ds[r.d]] = src[x * r.ss[r.a] + y * r.ss[r.c] + z * r.ss[r.d]];
+}
+
+template <class T>
+__global__ void relayout_tiles(T* __restrict__ dst, const T* __restrict__ src, RelayoutArgs r) {
+  __shared__ T tile[32][33];
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const long long c = blockIdx.z;
+  for (int i = threadIdx.y; i < 32; i += 8) {  // read: threadIdx.x runs along the source's unit-stride axis b
+    const int ia = a0 + i, ib = b0 + threadIdx.x;
+    if (ia < r.n[r.a] && ib < r.n[r.b]) tile[i][threadIdx.x] = src[ia * r.ss[r.a] + ib * r.ss[r.b] + c * r.ss[r.c]];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {  // write: threadIdx.x runs along the destination's unit-stride axis a
+    const int ia = a0 + threadIdx.x, ib = b0 + i;
+    if (ia < r.n[r.a] && ib < r.n[r.b]) dst[ia * r.ds[r.a] + ib * r.ds[r.b] + c * r.ds[r.c]] = tile[threadIdx.x][i];
+  }
+}
+
 }  // namespace
 
 struct b200_comm {
@@ -627,6 +786,73 @@ int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
   dim3 grid((unsigned)((row_bytes + 16 * 128 - 1) / (16 * 128)), (unsigned)(rows < 65535 ? rows : 65535));
   pack2d_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((char*)dst, dst_pitch, (const char*)src, src_pitch,
                                                           row_bytes, rows);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+// ---- data movement helpers of the storage / host-call path -------------------------------------------------------
+int b200_copy_box(void* dst, size_t dst_pitch, size_t dst_level_rows, const void* src, size_t src_pitch,
+                  size_t src_level_rows, size_t row_bytes, size_t rows, size_t levels, void* stream) {
+  if (!row_bytes || !rows || !levels) return B200_OK;
+  if (!dst || !src || row_bytes > dst_pitch || row_bytes > src_pitch || rows > dst_level_rows || rows > src_level_rows)
+    return fail(B200_ERR_INVALID, "b200_copy_box: box does not fit the pitched buffers");
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), src_pitch, row_bytes, src_level_rows);
+  p.dstPtr = make_cudaPitchedPtr(dst, dst_pitch, row_bytes, dst_level_rows);
+  p.extent = make_cudaExtent(row_bytes, rows, levels);
+  p.kind = cudaMemcpyDefault;
+  CU(cudaMemcpy3DAsync(&p, (cudaStream_t)stream));
+  return B200_OK;
+}
+
+int b200_relayout(void* dst, const void* src, int itemsize, const int32_t shape[3], const int64_t dst_strides[3],
+                  const int64_t src_strides[3], void* stream) {
+  if (!dst || !src || !shape || !dst_strides || !src_strides) return fail(B200_ERR_INVALID, "b200_relayout: null argument");
+  for (int d = 0; d < 3; ++d)
+    if (shape[d] <= 0) return B200_OK;
+  // a = unit-stride axis of the destination, b = unit-stride axis of the source (fall back to the smallest stride)
+  int a = 0, b = 0;
+  for (int d = 1; d < 3; ++d) {
+    if (llabs(dst_strides[d]) < llabs(dst_strides[a]) || shape[a] == 1) a = d;
+    if (llabs(src_strides[d]) < llabs(src_strides[b]) || shape[b] == 1) b = d;
+  }
+  RelayoutArgs r;
+  for (int d = 0; d < 3; ++d) {
+    r.n[d] = shape[d];
+    r.ds[d] = dst_strides[d];
+    r.ss[d] = src_strides[d];
+  }
+  r.a = a;
+  r.b = b;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a == b) {
+    // same fast axis: rows along a, coalesced on both sides
+    int o0 = (a + 1) % 3, o1 = (a + 2) % 3;
+    r.c = o0;
+    r.d = o1;
+    dim3 block(256), grid((unsigned)((shape[a] + 255) / 256), (unsigned)shape[o0], (unsigned)shape[o1]);
+    if (grid.y > 65535 || grid.z > 65535) return fail(B200_ERR_INVALID, "b200_relayout: extent too large");
+    switch (itemsize) {
+      case 1: relayout_rows<uint8_t><<<grid, block, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, r); break;
+      case 2: relayout_rows<uint16_t><<<grid, block, 0, st>>>((uint16_t*)dst, (const uint16_t*)src, r); break;
+      case 4: relayout_rows<uint32_t><<<grid, block, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, r); break;
+      case 8: relayout_rows<uint64_t><<<grid, block, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, r); break;
+      default: return fail(B200_ERR_INVALID, "b200_relayout: item size %d", itemsize);
+    }
+  } else {
+    r.c = 3 - a - b;
+    r.d = -1;
+    dim3 block(32, 8), grid((unsigned)((shape[a] + 31) / 32), (unsigned)((shape[b] + 31) / 32), (unsigned)shape[r.c]);
+    if (grid.y > 65535 || grid.z > 65535) return fail(B200_ERR_INVALID, "b200_relayout: extent too large");
+    switch (itemsize) {
+      case 1: relayout_tiles<uint8_t><<<grid, block, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, r); break;
+      case 2: relayout_tiles<uint16_t><<<grid, block, 0, st>>>((uint16_t*)dst, (const uint16_t*)src, r); break;
+      case 4: relayout_tiles<uint32_t><<<grid, block, 0, st>>>((uint32_t*)dst, (const uint32_t*)src, r); break;
+      case 8: relayout_tiles<uint64_t><<<grid, block, 0, st>>>((uint64_t*)dst, (const uint64_t*)src, r); break;
+      default: return fail(B200_ERR_INVALID, "b200_relayout: item size %d", itemsize);
+    }
+  }
   CU(cudaGetLastError());
   return B200_OK;
 }

@@ -14,9 +14,9 @@ launcher (kernels, halo exchanges, forked streams) into a CUDA graph:
         step.launch()                # one cudaGraphLaunch per time step
 
 Kernel arguments (device addresses, scalars, domain) are frozen at capture time: swap buffers by
-capturing one graph per buffer rotation, not by re-binding.  Every stencil must have run once with
-the same domain before it is captured (scratch for temporaries is allocated on first use) and must
-be built with `device_sync=False`.
+capturing one graph per buffer rotation, not by re-binding.  Stencils must be built with
+`device_sync=False`.  Scratch for temporaries is owned per (stencil, stream): a capture allocates what it
+needs, and the launcher keeps every buffer a captured graph points into alive until the stencil is unloaded.
 """
 
 from __future__ import annotations

@@ -141,24 +141,25 @@ class HostPipeline:
                 org[name] = (o[0], o[1], 0)
                 ranges[name] = slab_range(dev._base.numel(), dev._offset, dev.element_strides[2], o[2], k0, k1, c == 0, c == nch - 1)
             frozen = stencil.freeze(origin=org, domain=(self.domain[0], self.domain[1], k1 - k0))
-            self._steps.append((frozen, views, ranges))
+            self._steps.append((frozen, views, ranges, (k0, k1)))
+        self._origin = {n: tuple(int(x) for x in origin[n]) for n in self.fields}
         self.s_in, self.s_out = torch.cuda.Stream(), torch.cuda.Stream()
         self._ev_in = [torch.cuda.Event() for _ in self.chunks]
         self._ev_k = [torch.cuda.Event() for _ in self.chunks]
         self._torch = torch
         self.h2d_bytes = sum(self.fields[n]._base.numel() * self.fields[n].itemsize for n in self.inputs)
-        self.d2h_bytes = sum(self.fields[n]._base.numel() * self.fields[n].itemsize for n in self.outputs)
+        self.d2h_bytes = sum(int(np.prod(self.domain)) * self.fields[n].itemsize for n in self.outputs)
 
     def __call__(self, **kwargs) -> int:
         """kwargs: field name -> PinnedMirror (inputs are read, outputs are overwritten), scalar
         parameters by name.  Asynchronous: completion is ordered on the current stream."""
         torch = self._torch
         cur = torch.cuda.current_stream()
-        host = {n: kwargs[n].flat for n in set(self.inputs) | set(self.outputs)}
+        host = {n: _flat_of(kwargs[n]) for n in set(self.inputs) | set(self.outputs)}
         params = {n: kwargs[n] for n in self.stencil._param_names if n in kwargs}
         self.s_in.wait_stream(cur)  # device staging buffers are free once earlier work has finished
         launches = 0
-        for c, (frozen, views, ranges) in enumerate(self._steps):
+        for c, (frozen, views, ranges, (k0, k1)) in enumerate(self._steps):
             with torch.cuda.stream(self.s_in):
                 for n in self.inputs:
                     lo, hi = ranges[n]
@@ -168,9 +169,150 @@ class HostPipeline:
             launches += frozen(**views, **params)
             self._ev_k[c].record(cur)
             self.s_out.wait_event(self._ev_k[c])
-            with torch.cuda.stream(self.s_out):
-                for n in self.outputs:
-                    lo, hi = ranges[n]
-                    host[n][lo:hi].copy_(self.fields[n]._base[lo:hi], non_blocking=True)
+            for n in self.outputs:  # D2H of the compute domain only (strided DMA): the caller's halo is not touched
+                dev = self.fields[n]
+                copy_domain_box(_array_ptr(host[n], dev._offset), _array_ptr(dev._base, dev._offset), dev, self._origin[n],
+                                self.domain, k0, k1, int(self.s_out.cuda_stream))  # fmt: skip
         cur.wait_stream(self.s_out)
         return launches
+
+
+def copy_domain_box(dst_ptr: int, src_ptr: int, dev: "b2storage.DeviceArray", origin, domain, k0: int, k1: int, stream: int) -> None:
+    """Copy levels [k0, k1) of the COMPUTE DOMAIN of a pitched 3-D storage between two buffers of identical layout
+    (`dst_ptr` / `src_ptr` = addresses of array element [0,0,0] on either side) with one strided DMA (b200_copy_box):
+    what a stencil wrote travels back to the host, the halo of the caller's array stays untouched."""
+    import ctypes
+
+    from . import runtime
+
+    si, sj, sk = dev.element_strides
+    item = dev.itemsize
+    if si != 1 or sk % sj:
+        raise ValueError("b200 host path: storage is not in the pitched (2,1,0) layout")
+    off = (int(origin[0]) * si + int(origin[1]) * sj + (int(origin[2]) + k0) * sk) * item
+    runtime.check(runtime.load_library().b200_copy_box(
+        ctypes.c_void_p(dst_ptr + off), sj * item, sk // sj, ctypes.c_void_p(src_ptr + off), sj * item, sk // sj,
+        int(domain[0]) * item, int(domain[1]), int(k1 - k0), ctypes.c_void_p(stream)))  # fmt: skip
+
+
+def _array_ptr(flat, offset_elems: int) -> int:
+    return int(flat.data_ptr()) + int(offset_elems) * flat.element_size()
+
+
+def _flat_of(obj):
+    flat = getattr(obj, "_b200_flat", None)  # storage.HostArray
+    return flat if flat is not None else obj.flat  # PinnedMirror
+
+
+# ---- StencilObject.__call__ with HOST arrays ---------------------------------------------------------------------------
+def is_host_array(obj) -> bool:
+    """NumPy arrays (incl. storage.HostArray) and other objects that only export the host array interface."""
+    if isinstance(obj, np.ndarray):
+        return True
+    if isinstance(obj, b2storage.DeviceArray) or hasattr(obj, "__cuda_array_interface__"):
+        return False
+    if type(obj).__module__.startswith("torch"):
+        return not obj.is_cuda
+    return hasattr(obj, "__array_interface__")
+
+
+def _host_view(arg):
+    from . import runtime
+
+    arr = arg.numpy() if type(arg).__module__.startswith("torch") else np.asarray(arg)
+    if any(s % arr.itemsize for s in arr.strides):
+        raise ValueError("b200: strides must be multiples of the item size")
+    return arr, runtime.ArrayView(arr.ctypes.data, arr.shape, tuple(s // arr.itemsize for s in arr.strides), arr.dtype, arg)
+
+
+def host_call(stencil, field_args, parameter_args, domain, origin, *, validate_args=True, exec_info=None) -> None:
+    """One stencil application on arguments that live in HOST memory — an extension over the reference, whose GPU
+    backends refuse CPU arrays (storage/cartesian/utils.py:176-215): code written for `backend="numpy"` with plain
+    NumPy arrays runs unchanged on `backend="b200"`.
+
+    The fields are staged through cached device storages in the backend's layout: H2D of every field the stencil
+    reads, the kernels, D2H of every field it writes; the call returns when the results are in host memory.  When all
+    fields are `storage.HostArray`s (pinned, same pitched layout) and the K levels are independent, the three phases
+    are software-pipelined over K slabs (HostPipeline); any other host array takes one pageable copy + a device-side
+    re-layout per field.  There is no CPU compute path: the stencil always runs on the device."""
+    import torch
+
+    from . import stencil as b2stencil
+
+    host = {n: _host_view(a) for n, a in field_args.items() if a is not None and is_host_array(a)}
+    infos = {}
+    for n, a in field_args.items():
+        if a is None:
+            infos[n] = None
+        elif n in host:
+            infos[n] = b2stencil._ArgInfo(host[n][1], getattr(a, "__gt_origin__", None), None)
+        else:
+            infos[n] = b2stencil.extract_array_infos({n: a})[n]
+    origin = stencil._normalize_origins(infos, origin)
+    if domain is None:
+        domain = stencil._get_max_domain(infos, origin)
+    domain = tuple(int(d) for d in domain)
+    if validate_args:
+        stencil._validate_args(infos, parameter_args, domain, origin)
+    cache = stencil.__dict__.setdefault("_host_staging", {})
+    dev_args = dict(field_args)
+    for n, (arr, _view) in host.items():
+        fi = stencil.field_info[n]
+        dims = [a for a in "IJK" if a in fi.axes] + [str(d) for d in range(len(fi.data_dims))]
+        org = tuple(int(o) for o in origin[n]) + (0,) * (arr.ndim - len(origin[n]))
+        key = (n, arr.shape, arr.dtype.str, org)
+        dev = cache.get(key)
+        if dev is None:
+            if len(cache) > 4 * max(1, len(field_args)):
+                cache.clear()
+            dev = cache[key] = b2storage.empty(arr.shape, arr.dtype, aligned_index=org, dimensions=dims)
+        dev_args[n] = dev
+    reads = [n for n in host if stencil.field_info[n].access in ("READ", "READ_WRITE")]
+    writes = [n for n in host if stencil.field_info[n].access in ("WRITE", "READ_WRITE")]
+
+    def same_layout(n):
+        a = field_args[n]
+        return getattr(a, "_b200_flat", None) is not None and a._b200_layout == b2storage.layout_signature(dev_args[n])
+
+    used = [n for n, fi in stencil.field_info.items() if fi is not None and fi.access != "NONE" and field_args.get(n) is not None]
+    launches, path = None, "serial"
+    if all(n in host and same_layout(n) for n in used) and pipeline_supported(stencil.ir) is None and domain[2] >= 2:
+        pkey = ("pipeline", tuple((n, id(dev_args[n])) for n in used), domain, tuple(sorted((n, tuple(origin[n])) for n in used)))
+        pipe = cache.get(pkey)
+        if pipe is None:
+            try:
+                pipe = HostPipeline(stencil, {n: dev_args[n] for n in used}, origin=origin, domain=domain,
+                                    n_chunks=int(stencil.backend_options.get("host_chunks", 10)))  # fmt: skip
+            except ValueError:
+                pipe = False  # e.g. a field that is not 3-D: serial path
+            cache[pkey] = pipe
+        if pipe:
+            launches, path = pipe(**{n: field_args[n] for n in used}, **parameter_args), "pipeline"
+    if launches is None:
+        for n in reads:
+            if same_layout(n):
+                dev_args[n]._base.copy_(field_args[n]._b200_flat, non_blocking=True)
+            else:
+                dev_args[n][...] = host[n][0]
+        views = {n: (b2stencil.extract_array_infos({n: a})[n].view if a is not None else None) for n, a in dev_args.items()}
+        launches = stencil.compiled.run_views(views, stencil.compiled.pack_scalars(parameter_args), domain, origin)
+        from . import runtime
+
+        for n in writes:
+            dev = dev_args[n]
+            if same_layout(n) and dev.ndim == 3:
+                copy_domain_box(_array_ptr(field_args[n]._b200_flat, dev._offset), _array_ptr(dev._base, dev._offset), dev, origin[n],
+                                domain, 0, domain[2], runtime.current_stream_handle())  # fmt: skip
+    torch.cuda.current_stream().synchronize()
+    if path == "serial":
+        for n in writes:
+            dev = dev_args[n]
+            if not (same_layout(n) and dev.ndim == 3):
+                # the compute domain of the field (axes it has), every data-dimension entry
+                fi = stencil.field_info[n]
+                spatial = [d for d, m in zip(domain, fi.domain_mask) if m]
+                box = tuple(slice(int(o), int(o) + int(d)) for o, d in zip(origin[n], spatial))
+                host[n][0][box] = dev[box].get()
+    if exec_info is not None:
+        exec_info["b200_kernel_launches"] = launches
+        exec_info["b200_host_path"] = path

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = (
     "b200_stencil_run", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
     "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
-    "b200_halo_exchange", "b200_pack_2d",
+    "b200_halo_exchange", "b200_pack_2d", "b200_copy_box", "b200_relayout",
     "b200_graph_begin", "b200_graph_end", "b200_graph_num_nodes", "b200_graph_launch", "b200_graph_destroy",
 )  # fmt: skip
 
@@ -104,6 +104,8 @@ def load_library(build_if_missing: bool = True):
             "b200_comm_destroy": (ci, [vp]),
             "b200_halo_exchange": (ci, [vp, ctypes.POINTER(B200Halo), ci, ci, ci, vp]),
             "b200_pack_2d": (ci, [vp, cz, vp, cz, cz, cz, vp]),
+            "b200_copy_box": (ci, [vp, cz, cz, vp, cz, cz, cz, cz, cz, vp]),
+            "b200_relayout": (ci, [vp, vp, ci, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), vp]),
             "b200_graph_begin": (ci, [vp]),
             "b200_graph_end": (ci, [vp, pvp]),
             "b200_graph_num_nodes": (ci, [vp]),

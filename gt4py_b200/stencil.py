@@ -85,10 +85,16 @@ class B200Stencil:
     backend = "b200"
 
     def __init__(self, stencil_ir: Dict[str, Any], options: Optional[Dict[str, Any]] = None, *, name: Optional[str] = None):
+        opts = dict(options or {})
+        self._init_from_compiled(runtime.CompiledStencil(stencil_ir, opts, name=name or stencil_ir["name"]), opts)
+
+    def _init_from_compiled(self, compiled: "runtime.CompiledStencil", options: Dict[str, Any]) -> None:
+        """(also the entry for the gt4py plug-in: a mirror of a `backend="b200"` StencilObject around ITS compiled stencil)"""
+        stencil_ir = compiled.ir
         self.ir = stencil_ir
-        self.name = name or stencil_ir["name"]
-        self.backend_options = dict(options or {})
-        self.compiled = runtime.CompiledStencil(stencil_ir, self.backend_options, name=self.name)
+        self.name = compiled.name
+        self.backend_options = dict(options)
+        self.compiled = compiled
         self.field_info: Dict[str, Optional[FieldInfo]] = {
             n: (FieldInfo(fi) if fi is not None else None) for n, fi in stencil_ir["field_info"].items()
         }
@@ -266,6 +272,14 @@ class B200Stencil:
     def _call_run(self, field_args, parameter_args, domain, origin, *, validate_args=True, exec_info=None):
         if exec_info is not None:
             exec_info["call_run_start_time"] = time.perf_counter()
+        from . import hostpipe
+
+        if any(a is not None and hostpipe.is_host_array(a) for a in field_args.values()):
+            # arguments in HOST memory: staged through device storages (H2D, kernels, D2H; K-slab pipelined when possible)
+            hostpipe.host_call(self, field_args, parameter_args, domain, origin, validate_args=validate_args, exec_info=exec_info)
+            if exec_info is not None:
+                exec_info["call_run_end_time"] = time.perf_counter()
+            return
         infos = extract_array_infos(field_args)
         key = hash(
             (

@@ -151,6 +151,12 @@ def compute_layout(shape, lmap, itemsize: int, alignment_elems: int, aligned_ind
     return tuple(strides), total, lead
 
 
+def _is_full_key(key) -> bool:
+    if key is Ellipsis or (isinstance(key, slice) and key == slice(None)):
+        return True
+    return isinstance(key, tuple) and all(k is Ellipsis or (isinstance(k, slice) and k == slice(None)) for k in key)
+
+
 class DeviceArray:
     """ndarray-like view of device memory (I-contiguous pitched buffer owned by a torch tensor)."""
 
@@ -229,6 +235,9 @@ class DeviceArray:
         elif isinstance(value, np.generic):  # NumPy scalars (gt4py's ones()/full() assign `dtype(1)`): torch wants Python scalars
             value = value.item()
         elif isinstance(value, np.ndarray):
+            if (_is_full_key(key) and value.shape == self.shape and 1 <= self.ndim <= 3 and self.dtype.itemsize in (1, 2, 4, 8)
+                    and self._base.is_cuda):  # fmt: skip
+                return self._upload(value)
             value = torch.from_numpy(np.ascontiguousarray(value)).to(self._base.device, non_blocking=False)
         elif hasattr(value, "__cuda_array_interface__") and not isinstance(value, torch.Tensor):
             value = torch.as_tensor(value, device=self._base.device)
@@ -237,6 +246,30 @@ class DeviceArray:
         if isinstance(value, torch.Tensor):
             value = value.to(dtype=_torch_dtype(self.dtype))
         self.torch()[key] = value
+
+    def _upload(self, value: np.ndarray) -> None:
+        """Whole-array upload of a host array (reference: storage/cartesian/interface.py:323-325 `storage[...] = data`):
+        ONE contiguous H2D copy of the data as it lies in host memory, then a re-layout on the device by the launcher's
+        tiled transpose kernel (b200_relayout; coalesced on both sides — torch's element-wise strided copy reached
+        0.44 TB/s here)."""
+        import ctypes
+
+        from . import runtime
+
+        torch = _torch()
+        src = np.ascontiguousarray(value.astype(self.dtype, copy=False))
+        if src.dtype == np.bool_:
+            src = src.view(np.uint8)
+        staged = torch.from_numpy(src).to(self._base.device, non_blocking=False)
+        pad = 3 - self.ndim
+        shape = (ctypes.c_int32 * 3)(*self.shape, *([1] * pad))
+        ds = (ctypes.c_int64 * 3)(*self._estrides, *([0] * pad))
+        ss = (ctypes.c_int64 * 3)(*staged.stride(), *([0] * pad))
+        lib = runtime.load_library()
+        stream = runtime.current_stream_handle()
+        runtime.check(lib.b200_relayout(ctypes.c_void_p(self.data_ptr), ctypes.c_void_p(staged.data_ptr()), self.dtype.itemsize,
+                                        shape, ds, ss, ctypes.c_void_p(stream)))  # fmt: skip
+        runtime.check(lib.b200_stream_synchronize(ctypes.c_void_p(stream)))  # `staged` may be freed on return
 
     def transpose(self, *axes):
         if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
@@ -488,6 +521,49 @@ def from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, d
     out = empty(shape, dtype, backend=backend, aligned_index=aligned_index, dimensions=dimensions, device=device)
     out[...] = src.astype(out.dtype, copy=False)
     return out
+
+
+# ---- host-side storages in the backend's layout ---------------------------------------------------------------------
+class HostArray(np.ndarray):
+    """NumPy array over PINNED host memory laid out exactly like the device storage `empty()` returns for the same
+    (shape, dtype, aligned_index, dimensions): pitched rows, I unit-stride, aligned origin.  A b200 stencil called with
+    such arrays (`stencil(host_in, host_out, ...)`, see hostpipe.host_call) moves them with ONE contiguous DMA per
+    field / K slab instead of a pageable copy followed by a re-layout on the device.  Slices are plain views."""
+
+    _b200_flat = None  # the whole pinned buffer (1-D torch tensor), transferred as it is
+    _b200_layout = None  # (shape, element strides, lead offset, element count): equal layouts <=> flat copies are legal
+
+    def __array_finalize__(self, obj):
+        self._b200_flat = None
+        self._b200_layout = None
+
+
+def host_empty(shape, dtype=np.float64, *, backend: str = "b200", aligned_index=None, dimensions=None, pinned: bool = True) -> HostArray:
+    """Host counterpart of `empty()`: same layout algebra (reference allocators.py:205-254), page-locked memory."""
+    if backend != "b200":
+        raise RuntimeError(f"Storage preset '{backend}' is not handled by gt4py_b200.storage.")
+    torch = _torch()
+    aligned_index, shape, dtype, dimensions = normalize_storage_spec(aligned_index, shape, dtype, dimensions)
+    estrides, total, lead = compute_layout(shape, layout_map(dimensions), np.dtype(dtype).itemsize, ALIGNMENT_ELEMENTS, aligned_index)
+    flat = torch.zeros(total + lead, dtype=_torch_dtype(np.dtype(dtype)))
+    if pinned and torch.cuda.is_available():
+        flat = flat.pin_memory()
+    arr = torch.as_strided(flat, tuple(shape), tuple(estrides), flat.storage_offset() + lead).numpy().view(HostArray)
+    arr._b200_flat = flat
+    arr._b200_layout = (tuple(shape), tuple(estrides), int(lead), int(total + lead))
+    return arr
+
+
+def host_from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, dimensions=None, pinned: bool = True) -> HostArray:
+    src = np.asarray(data)
+    out = host_empty(src.shape, dtype or src.dtype, backend=backend, aligned_index=aligned_index, dimensions=dimensions, pinned=pinned)
+    out[...] = src
+    return out
+
+
+def layout_signature(arr: "DeviceArray"):
+    """(shape, element strides, lead offset, element count) of a device storage as allocated by `empty()`."""
+    return (tuple(arr.shape), tuple(arr.element_strides), int(arr._offset), int(arr._base.numel()))
 
 
 def cpu_copy(array) -> np.ndarray:

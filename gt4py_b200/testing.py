@@ -38,6 +38,7 @@ CASE_SPECS: Dict[str, Dict[str, Any]] = {
     "col_multiwrite_f32": {"params": {"w": np.float32(0.625)}},
     "ints_bools": {"inputs": "ints"},
     "casts": {"inputs": "ints"},
+    "sections_koff_f64": {"domain": (70, 40, 6)},
 }
 
 

@@ -100,9 +100,9 @@ int b200_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises o
  *      reference pays its Python call path, stencil_object.py:296-643, on every one of them) -------
  * Everything enqueued on `stream` between begin and end — b200_stencil_run launches, halo exchanges,
  * work on streams forked/joined with b200_event_record + b200_stream_wait_event — is captured instead
- * of executed; kernel arguments are frozen at capture time.  A stencil whose scratch is not yet
- * allocated for the domain must be called once before capture (b200_stencil_run fails loudly
- * otherwise).  b200_graph_launch replays the whole sequence with one driver call. */
+ * of executed; kernel arguments are frozen at capture time.  Scratch for temporaries is owned per (stencil,
+ * stream): a capture allocates what it needs, and a buffer referenced by a captured graph stays alive until
+ * b200_stencil_unload.  b200_graph_launch replays the whole sequence with one driver call. */
 typedef struct b200_graph b200_graph_t;
 int b200_graph_begin(void* stream);
 int b200_graph_end(void* stream, b200_graph_t** out);
@@ -127,6 +127,20 @@ int b200_halo_exchange(b200_comm_t* comm, const b200_halo_t* halos, int n_halos,
 /* Strided slab <-> contiguous staging buffer copy kernels (J-halo slabs of a (2,1,0)-layout field
  * are nK separate chunks): rows × row_bytes, source/destination pitch in bytes. */
 int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);
+
+
+/* ---- data movement of the storage / host-call path (replaces the cupy copies of the reference's storage front-end,
+ *      storage/cartesian/interface.py:264-327, storage/cartesian/utils.py:237-279) ------------------------------------ */
+/* Copy a box of `levels` x `rows` rows of `row_bytes` bytes between two pitched buffers (host or device, any direction)
+ * with ONE strided DMA (cudaMemcpy3DAsync): only the compute domain of an output travels back to the host, its halo
+ * in the caller's array stays untouched.  *_pitch = bytes between rows, *_level_rows = rows between levels. */
+int b200_copy_box(void* dst, size_t dst_pitch, size_t dst_level_rows, const void* src, size_t src_pitch,
+                  size_t src_level_rows, size_t row_bytes, size_t rows, size_t levels, void* stream);
+/* dst[i,j,k] = src[i,j,k] for a 3-D array of `itemsize`-byte elements given ELEMENT strides on both sides (device
+ * memory): the upload of a C-ordered host array into the pitched I-unit-stride storage layout.  Tiled through shared
+ * memory when the unit-stride axes differ (coalesced on both sides). */
+int b200_relayout(void* dst, const void* src, int itemsize, const int32_t shape[3], const int64_t dst_strides[3],
+                  const int64_t src_strides[3], void* stream);
 
 #ifdef __cplusplus
 }

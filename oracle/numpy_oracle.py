@@ -272,11 +272,29 @@ def _bound_abs(b, n, default):
     return off if level == "start" else n + off
 
 
+class _LazyMask:
+    """A mask that is RE-EVALUATED by every statement it guards: how the numpy backend lowers `while` — the loop
+    condition (AND the enclosing masks) is inlined as the `np.where` condition of every statement of the body
+    (gtc/numpy/oir_to_npir.py:149-185: visit_While passes `mask=cond_expr` down, visit_MaskStmt ANDs onto it,
+    visit_AssignStmt wraps the right-hand side in a VectorTernaryOp on that expression)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, ctx, reg):
+        return self.fn(ctx, reg)
+
+
+def _mask_now(mask, ctx, reg):
+    return mask(ctx, reg) if isinstance(mask, _LazyMask) else mask
+
+
 def _assign(stmt, ctx, reg, mask):
     left = stmt["left"]
     i0, i1, j0, j1, k0, k1 = reg
     if i1 <= i0 or j1 <= j0 or k1 <= k0:
         return
+    mask = _mask_now(mask, ctx, reg)
     rhs = _eval(stmt["right"], ctx, reg)
     name = left["name"]
     if name in ctx.locals:
@@ -311,21 +329,23 @@ def _exec_stmts(stmts, ctx, reg, mask):
         if t == "assign":
             _assign(s, ctx, reg, mask)
         elif t == "mask":
-            m = _eval(s["mask"], ctx, reg)
-            if mask is not None:
-                m = np.bitwise_and(mask, m)
+            if isinstance(mask, _LazyMask):  # inside a while body: the whole mask chain is re-evaluated per statement
+                m = _LazyMask(lambda c, r, outer=mask, e=s["mask"]: np.bitwise_and(outer(c, r), _eval(e, c, r)))
+            else:
+                m = _eval(s["mask"], ctx, reg)
+                if mask is not None:
+                    m = np.bitwise_and(mask, m)
             _exec_stmts(s["body"], ctx, reg, m)
         elif t == "while":
-            # Per-point `while (cond) { body }` (the semantics of the reference's debug / gt:* backends).
-            # NOTE: the numpy backend inlines `cond` as the mask of every body statement and so
-            # re-evaluates it mid-iteration (oir_to_npir.py:176-185); both agree whenever the loop
-            # variable is updated by the last statement of the body, which is what the fixtures do.
-            active = _eval(s["cond"], ctx, reg)
-            if mask is not None:
-                active = np.bitwise_and(mask, active)
-            while np.any(active):
+            # numpy-backend semantics (north_star's oracle): `while np.any(cond): <every body statement masked by the
+            # re-evaluated cond>` (npir_codegen.py:252-267).  Equal to a per-point `while` whenever the loop variable is
+            # updated by the last statement of the body; fixture while_first_f64 pins the case where it is not.
+            if mask is None:
+                active = _LazyMask(lambda c, r, e=s["cond"]: _eval(e, c, r))
+            else:
+                active = _LazyMask(lambda c, r, outer=mask, e=s["cond"]: np.bitwise_and(_mask_now(outer, c, r), _eval(e, c, r)))
+            while np.any(active(ctx, reg)):
                 _exec_stmts(s["body"], ctx, reg, active)
-                active = np.bitwise_and(active, _eval(s["cond"], ctx, reg))
         elif t == "hregion":
             i0, i1, j0, j1, k0, k1 = reg
             ri0 = max(i0, _bound_abs(s["i"][0], ctx.nI, -(10**9)))
@@ -335,6 +355,8 @@ def _exec_stmts(stmts, ctx, reg, mask):
             if ri1 <= ri0 or rj1 <= rj0:
                 continue
             sub = (ri0, ri1, rj0, rj1, k0, k1)
+            if isinstance(mask, _LazyMask):
+                raise NotImplementedError("horizontal region inside a while loop")
             m = mask
             if m is not None and isinstance(m, np.ndarray) and m.ndim == 3:
                 m = m[

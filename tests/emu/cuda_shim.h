@@ -15,6 +15,8 @@
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)
+#define __shared__ static /* warps of a CTA run one after the other, lanes of a warp are threads of this process */
+#define __align__(n) __attribute__((aligned(n)))
 
 struct emu_uint3 { unsigned x, y, z; };
 extern thread_local emu_uint3 threadIdx, blockIdx;
@@ -50,6 +52,7 @@ namespace emu {
 unsigned long long exchange(unsigned long long bits, int src_lane);  // value of `bits` held by src_lane
 bool any(bool pred);
 int lane();
+void fail(const char* what);  // device trap / hang: abort the test run with a message
 void trace(int slot);  // B200_TRACE: per-path counters, read back with emu_trace_read()
 template <class T> inline T shfl(T v, int src) {
   unsigned long long b = 0; std::memcpy(&b, &v, sizeof(T));
@@ -60,4 +63,5 @@ template <class T> inline T shfl(T v, int src) {
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l - d >= 0 ? l - d : l); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l + d < 32 ? l + d : l); }
 inline bool __any_sync(unsigned, bool p) { return emu::any(p); }
+inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu::any(false); }
 inline bool __all_sync(unsigned, bool p) { return !emu::any(!p); }

@@ -77,7 +77,7 @@ class EmuStencil:
     def trace(self, reset=True):
         """B200_TRACE counters: {0: steady-loop trips (pure), 1: steady-loop trips (edge/fastall),
         2: general march steps, 3: steady-loop trips (interior), 4: interior prologue/epilogue steps} of the streaming kernels since the last reset."""
-        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(5)}
+        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(6)}
 
     # ---- mirror of launcher.cu ------------------------------------------------------------------
     def _temp_layout(self, f, dom):
@@ -125,7 +125,8 @@ class EmuStencil:
         nf = len(plan["fields"])
         keep = []
         fa = []
-        for f in plan["fields"]:
+        geo = {}  # field index -> (address of array element [0,0,0], shape3, strides, origin3): what launcher.cu encodes tensor maps from
+        for fidx, f in enumerate(plan["fields"]):
             item = f["itemsize"]
             if f["kind"] == "dead":
                 fa.append((0, [0] * 7, 0, 0, 0))
@@ -138,6 +139,9 @@ class EmuStencil:
                 base += (-base) % 16
                 ptr = base + (org[0] * s[0] + org[1] * s[1]) * item
                 fa.append((ptr, s, 0, nk, self._vec(ptr, s, item)))
+                e = f["extent"] or [[0, 0], [0, 0]]
+                pitch, nj = (s[1] if f["dims"][1] else nelem), (dom[1] + e[1][1] - e[1][0] if f["dims"][1] else 1)
+                geo[fidx] = (base, [pitch if f["dims"][0] else 1, nj, nk], s, org)
                 continue
             arr = fields.get(f["name"])
             if arr is None:
@@ -155,6 +159,7 @@ class EmuStencil:
             ptr = arr.ctypes.data + sum(o3[a] * s[a] for a in range(3)) * item
             klo, khi = (-o3[2], shape3[2] - o3[2]) if f["dims"][2] else (0, 1)
             fa.append((ptr, s, klo, khi, self._vec(ptr, s, item)))
+            geo[fidx] = (arr.ctypes.data, shape3, s, o3)
         scal = b""
         if plan["scalars"]:
             fmt_of = {"bool": "?", "int8": "b", "int16": "h", "int32": "i", "int64": "q", "float32": "f", "float64": "d"}
@@ -177,6 +182,28 @@ class EmuStencil:
             for ptr, s, klo, khi, vec in (fa if fa else [(0, [0] * 7, 0, 0, 0)]):
                 b += struct.pack("<Q7q4i", ptr, *s, klo, khi, vec, 0)
             b += scal
+            tmaps = plan.get("tmaps", [])
+            if tmaps:  # mirror of launcher.cu encode_tmaps (emulated map layout: b200_device.cuh, B200_HOST_EMU)
+                b += b"\0" * ((-len(b)) % 64)
+                offs = b""
+                for t in tmaps:
+                    f = plan["fields"][t["field"]]
+                    g, (_p, _s, _klo, _khi, vec) = geo.get(t["field"]), fa[t["field"]]
+                    if g is None or not vec:
+                        b += b"\0" * 128
+                        offs += struct.pack("<4i", 0, 0, 0, 0)
+                        continue
+                    start, shape3, s, o3 = g
+                    item = f["itemsize"]
+                    base = start - start % 16
+                    extra = (start - base) // item
+                    has_k = bool(f["dims"][2])
+                    dims = [shape3[0] + extra, shape3[1], shape3[2] if has_k else 1]
+                    sk = s[2] * item if has_k else s[1] * item * shape3[1]
+                    m = struct.pack("<Q3q3q3i", base, *dims, item, s[1] * item, sk, t["box"][0], t["box"][1], item)
+                    b += m + b"\0" * (128 - len(m))
+                    offs += struct.pack("<4i", o3[0] + extra, o3[1], o3[2] if has_k else 0, 1 if has_k else 0)
+                b += offs
             return b + b"\0" * ((-len(b)) % 8)
 
         def resolve(bound):
@@ -195,11 +222,14 @@ class EmuStencil:
                 V = tile[2]
                 x0, x1 = i_lo + e[0][0], i_hi + e[0][1]
                 qx0 = x0 // V  # floor
-                nseg = -(-(x1 - qx0 * V) // tile[0])
+                nseg = -(-(x1 - (qx0 - int(k.get("qshift", 0))) * V) // tile[0])
                 ntj = -(-ny // tile[1])
                 grid = [-(-(nseg * ntj * nz) // k["block"][1]), 1, 1]
             data = blob(k_lo, k_hi)
-            buf = ctypes.create_string_buffer(data, len(data))
+            raw = ctypes.create_string_buffer(len(data) + 64)  # the argument block is 64-byte aligned (tensor maps)
+            addr = ctypes.addressof(raw)
+            buf = ctypes.c_void_p(addr + (-addr) % 64)
+            ctypes.memmove(buf, data, len(data))
             fn = getattr(self.lib, f"emu_call_{k['name']}")
             g = (ctypes.c_uint * 3)(*grid)
             bdim = (ctypes.c_uint * 3)(*k["block"])

@@ -1,5 +1,7 @@
 // Warp-lockstep CPU runner for generated kernels (see cuda_shim.h).  Test infrastructure only.
 #include <barrier>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <thread>
 #include <vector>
@@ -32,6 +34,11 @@ bool any(bool pred) {
   for (int i = 0; i < g_active; ++i) r = r || g_votes[i];
   g_bar->arrive_and_wait();
   return r;
+}
+void fail(const char* what) {
+  fprintf(stderr, "b200 emulator: %s\n", what);
+  fflush(stderr);
+  abort();
 }
 static long long g_trace[8];
 void trace(int slot) { __atomic_fetch_add(&g_trace[slot & 7], 1LL, __ATOMIC_RELAXED); }

@@ -38,6 +38,9 @@ class _Event:
 class _Stream:
     cuda_stream = 0
 
+    def synchronize(self):
+        pass
+
     def wait_stream(self, other):
         pass
 
@@ -109,11 +112,6 @@ def install(mp) -> None:
 
     def run_descs(self, descs, scalars, domain, *, stream=None, subbox=None):
         if capture["on"]:  # CUDA-graph capture: nothing executes, the launches are recorded with frozen arguments
-            tgt = self.specialized_for(descs)
-            if any(f["kind"] == "temp" for f in tgt.plan["fields"]) and getattr(tgt, "_emu_domain", None) != tuple(domain):
-                # launcher.cu: scratch for temporaries cannot be allocated while the stream is being captured
-                raise runtime.B200Error(f"b200 launcher error -1: stencil {tgt.name} needs scratch but the stream is being captured: "
-                                        "call it once with this domain before capturing")
             frozen_descs = type(descs).from_buffer_copy(descs)
             capture["calls"].append((self, frozen_descs, bytes(scalars), tuple(domain), None if subbox is None else tuple(subbox)))
             n = sum(1 for st in self.specialized_for(descs).plan["steps"] if st["t"] == "launch")
@@ -157,6 +155,26 @@ def install(mp) -> None:
 
         def b200_event_elapsed_ms(self, start, stop, ref):
             ctypes.cast(ref, ctypes.POINTER(ctypes.c_float))[0] = 0.01
+            return 0
+
+        def b200_copy_box(self, dst, dpitch, dlevel_rows, src, spitch, slevel_rows, row_bytes, rows, levels, stream):
+            dst, src = int(getattr(dst, "value", dst)), int(getattr(src, "value", src))
+            for lev in range(int(levels)):
+                for r in range(int(rows)):
+                    ctypes.memmove(dst + (lev * dlevel_rows + r) * dpitch, src + (lev * slevel_rows + r) * spitch, int(row_bytes))
+            return 0
+
+        def b200_relayout(self, dst, src, itemsize, shape, ds, ss, stream):
+            dst, src = int(getattr(dst, "value", dst)), int(getattr(src, "value", src))
+            dt = np.dtype(f"u{itemsize}")
+            shp = [int(shape[d]) for d in range(3)]
+
+            def view(ptr, st):
+                span = 1 + sum((n - 1) * abs(int(st[d])) for d, n in enumerate(shp))
+                buf = (ctypes.c_char * (span * itemsize)).from_address(ptr)
+                return np.ndarray(shp, dt, buffer=buf, strides=[int(st[d]) * itemsize for d in range(3)])
+
+            view(dst, ds)[...] = view(src, ss)
             return 0
 
         def b200_graph_begin(self, stream):

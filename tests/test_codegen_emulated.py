@@ -218,3 +218,68 @@ def test_loop_fusion_legality_rules():
     both = cs._fuse(loop([("t", fld("x"))]), loop([("y", fld("t"))], (("start", 1), ("end", -1))))
     assert [(s["interval"], len(s["hes"])) for s in both["sections"]] == [
         ([["start", 0], ["start", 1]], 1), ([["start", 1], ["end", -1]], 2), ([["end", -1], ["end", 0]], 1)]  # fmt: skip
+
+
+# ---- hazards the reference's own checks never let through, but hand-built / fused IRs can ---------------------------------
+def _inplace_diffusion_ir():
+    """`t = x; x = t[-1,0,0] + t[1,0,0] + t[0,-1,0] + t[0,1,0]`: the incoming state of x is needed on the neighbours' cells
+    while x is being overwritten.  gt4py rejects it at GTIR->OIR ("non-zero read extent on written fields",
+    gtc/gtir_to_oir.py:19-46); an IR built by hand (or by a fusion tool) must still run correctly."""
+    f64 = "float64"
+
+    def fa(name, off=(0, 0, 0)):
+        return {"t": "field", "name": name, "off": list(off), "data_index": [], "dtype": f64}
+
+    def add(a, b):
+        return {"t": "binary", "op": "+", "left": a, "right": b, "dtype": f64}
+
+    hes = [
+        {"body": [{"t": "assign", "left": fa("t"), "right": fa("x")}], "extent": [[-1, 1], [-1, 1]], "locals": []},
+        {"body": [{"t": "assign", "left": fa("x"),
+                   "right": add(add(add(fa("t", (-1, 0, 0)), fa("t", (1, 0, 0))), fa("t", (0, -1, 0))), fa("t", (0, 1, 0)))}],
+         "extent": [[0, 0], [0, 0]], "locals": []},
+    ]  # fmt: skip
+    decl = {"data_dims": [], "dims": [True, True, True], "dtype": f64}
+    return {
+        "t": "stencil", "name": "inplace_diffuse_f64", "ir_version": 1, "variant": "staged", "options": {},
+        "domain_info": {"min_k": 0}, "parameter_info": {},
+        "field_info": {"x": {"access": "READ_WRITE", "axes": ["I", "J", "K"], "boundary": [[1, 1], [1, 1], [0, 0]], "data_dims": [], "dtype": f64}},
+        "params": [{**decl, "name": "x", "t": "field"}],
+        "temporaries": [{**decl, "name": "t", "extent": [[-1, 1], [-1, 1]]}],
+        "loops": [{"order": "parallel", "caches": [], "sections": [{"interval": [["start", 0], ["end", 0]], "hes": hes}]}],
+    }  # fmt: skip
+
+
+@pytest.mark.parametrize("options", [{"strategy": "auto"}, {"strategy": "point"}, {"strategy": "auto", "interior_loop": True, "tma": 2}])
+def test_in_place_update_through_a_temporary_on_a_multi_tile_domain(options):
+    """the streaming generator kept `x` as an input stream with halo lanes / rows AND stored it in the
+    same kernel: warps read cells their neighbours had already overwritten (1792 wrong cells on this domain).  Such a
+    loop is no longer streamable; the point generator splits it at the hazard."""
+    st = _inplace_diffusion_ir()
+    domain = (300, 150, 2)
+    rng = np.random.default_rng(3)
+    x = rng.random((domain[0] + 2, domain[1] + 2, domain[2]))
+    origins = {"x": (1, 1, 0)}
+    ref = {"x": x.copy()}
+    numpy_oracle.run(st, ref, {}, domain, origins)
+    es = EmuStencil(st, options, name="inplace_diffuse")
+    got = {"x": x.copy()}
+    es.run(got, {}, domain, origins, layout="b200", guard="end")
+    np.testing.assert_array_equal(got["x"], ref["x"])
+    assert len(es.plan["kernels"]) >= 2 and all(k["kind"] != "stream" for k in es.plan["kernels"])
+
+
+def test_parallel_sections_coupled_through_a_k_offset_are_separate_ordered_launches():
+    """ADVICE r1 (medium): one kernel for all sections of a PARALLEL loop runs them concurrently (K on blockIdx.z);
+    `interval(0,2): b = a*2; interval(2,None): c = b[0,0,-2] + 1` (one vertical loop after AdjacentLoopMerging) needs
+    the first section finished before the second starts."""
+    for variant in ("default", "staged"):
+        st = testing.load_ir("sections_koff_f64", variant)
+        assert len(st["loops"]) == 1 and len(st["loops"][0]["sections"]) == 2  # the reference merged the two computations
+        for strategy in ("point", "auto"):
+            es = run_emulated("sections_koff_f64", variant, {"strategy": strategy}, check_golden=True)
+            launches = [s for s in es.plan["steps"] if s["t"] == "launch"]
+            assert len(launches) == 2, (variant, strategy, es.plan["steps"])
+    # independent sections still share one kernel
+    es = run_emulated("k_intervals_f64", "default", {"strategy": "point"})
+    assert len([s for s in es.plan["steps"] if s["t"] == "launch"]) == 1

@@ -170,3 +170,20 @@ def test_hdiff_smooth_analytic_field(options):
     np.testing.assert_array_equal(dev["out_field"].get(), ref["out_field"])
     box = tuple(slice(o, o + d) for o, d in zip(origins["out_field"], domain))
     assert np.abs(ref["out_field"][box] - ref["in_field"][tuple(slice(o, o + d) for o, d in zip(origins["in_field"], domain))]).max() > 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.bool_, np.int64])
+@pytest.mark.parametrize("shape,dims,ai", [((70, 45, 9), None, (2, 3, 0)), ((33, 17), ("I", "J"), (1, 1)), ((19,), ("K",), (0,)),
+                                            ((64, 64, 16), None, (0, 0, 0)), ((5, 3, 130), None, (1, 0, 0))])
+def test_from_array_upload_goes_through_the_relayout_kernel(dtype, shape, dims, ai):
+    """storage.from_array: one contiguous H2D + the launcher's tiled re-layout kernel (b200_relayout) == the host data,
+    for C-ordered, Fortran-ordered and sliced sources; the padding of the storage stays zero"""
+    from gt4py_b200 import storage
+
+    rng = np.random.default_rng(7)
+    src = (rng.random(shape) * 100).astype(dtype) if dtype != np.bool_ else rng.random(shape) > 0.5
+    for host in (src, np.asfortranarray(src), np.ascontiguousarray(np.flip(src, 0))[::-1]):
+        dev = storage.from_array(host, aligned_index=ai, dimensions=dims)
+        assert dev.dtype == np.dtype(dtype) and dev.shape == shape
+        np.testing.assert_array_equal(dev.get(), src)
+        assert float(dev._base.to(dtype=__import__("torch").float64).abs().sum()) == float(np.abs(src.astype(np.float64)).sum())

@@ -380,6 +380,35 @@ def while_f64(a: F64, b: F64):
         b = n + x
 
 
+@case("while_first_f64")
+def while_first_f64(a: F64, b: F64):
+    # the loop variable is updated FIRST: the reference numpy backend re-evaluates the loop condition as the mask of
+    # every body statement (gtc/numpy/oir_to_npir.py:176-185), so `n` misses the increment of the iteration in which
+    # x crosses 1.0 — unlike a per-point `while`.  north_star's oracle is the numpy backend: b200 reproduces it.
+    with computation(PARALLEL), interval(...):
+        x = a
+        n = 0.0
+        while x < 1.0:
+            x = x * 1.5 + 0.01
+            n = n + 1.0
+        b = n + x
+
+
+@case("while_masked_f64")
+def while_masked_f64(a: F64, b: F64):
+    with computation(PARALLEL), interval(...):
+        x = a
+        n = 0.0
+        if a > 0.25:
+            while x < 2.0:
+                x = x * 1.25 + 0.125
+                if x > 1.0:
+                    n = n + 2.0
+                else:
+                    n = n + 1.0
+        b = n * 10.0 + x
+
+
 @case("regions_f64")
 def regions_f64(a: F64, b: F64):
     with computation(PARALLEL), interval(...):
@@ -665,3 +694,14 @@ def fuse_partial_f64(a: F64, b: F64, c: F64):
     with computation(PARALLEL), interval(...):
         b = v[0, -1, 0] + u[0, 0, 0]
         c = v[-1, 0, 0]
+
+
+@case("sections_koff_f64")
+def sections_koff_f64(a: F64, b: F64, c: F64):
+    # adjacent-interval PARALLEL computations are merged into ONE vertical loop by the reference
+    # (AdjacentLoopMerging); the second section reads at a K offset what the first one writes
+    with computation(PARALLEL):
+        with interval(0, 2):
+            b = a * 2.0
+        with interval(2, None):
+            c = b[0, 0, -2] + 1.0
