@@ -283,6 +283,11 @@ class B200Backend(BaseBackend):
         "stcs": {"versioning": True, "type": bool},  # streaming (evict-first) stores
         "ldcs": {"versioning": True, "type": bool},  # streaming loads instead of the read-only path
         "min_blocks": {"versioning": True, "type": int},
+        "tma": {"versioning": True, "type": int},  # bulk-async variant: shared-memory ring slots (trips) per warp
+        "tma_rows": {"versioning": True, "type": int},
+        "tma_mode": {"versioning": True, "type": str},  # "tensor" (cp.async.bulk.tensor) | "bulk" (one cp.async.bulk per row)
+        "tma_smem_kb": {"versioning": True, "type": int},
+        "halo_wait": {"versioning": True, "type": bool},  # multi-GPU: boundary tiles wait for the neighbours' pushed halo rows
         "row_pointers": {"versioning": True, "type": bool},
         "fuse_columns": {"versioning": True, "type": bool},
         "fuse_loops": {"versioning": True, "type": bool},
@@ -301,7 +306,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "extra_opt_flags", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

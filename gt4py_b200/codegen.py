@@ -327,7 +327,7 @@ def _sections_k_coupled(loop) -> bool:
     """A section of this PARALLEL loop reads, at a K offset (or a variable / absolute K index), a field that ANOTHER
     section of the loop writes.  The reference merges adjacent-interval PARALLEL loops without a dependency check
     (gtc/passes/oir_optimizations/vertical_loop_merging.py, AdjacentLoopMerging) and its numpy backend runs the sections
-    one after the other, so `interval(0,2): b = a; interval(2,None): c = b[0,0,-2]` is legal and ordered: the sections
+    one after the other, so `interval(0,1): b = a; interval(1,None): c = b[0,0,-1]` is legal and ordered: the sections
     must then be separate launches, in order (one kernel with K on blockIdx.z would race across levels)."""
     secs = loop["sections"]
     if len(secs) < 2:

@@ -296,8 +296,10 @@ class StreamKernel:
         # bulk-async variant: a warp row is copied by ONE cp.async.bulk (16-byte aligned source, size a multiple of
         # 16): when a vector is only 8 bytes (fp32 x 2) the segments must start at even vector indices
         isz = min(sizes)
-        self.tma_tensor = self.opts.get("tma_mode", "tensor") == "tensor"  # tensor-map copies have no alignment rule for the start
-        self.qalign = 2 if (self.opts.get("tma") and not self.tma_tensor and V * isz == 8) else 1
+        self.tma_tensor = self.opts.get("tma_mode", "tensor") == "tensor"
+        # (both copy flavours: a tensor-map copy whose box starts at an 8-byte-aligned element is an illegal
+        #  instruction on the device — measured, profiles/README.md r02e)
+        self.qalign = 2 if (self.opts.get("tma") and V * isz == 8) else 1
         if self.qalign == 2 and self.SQ % 2:
             self.SQ -= 1
         self._choose_windows()
@@ -396,9 +398,22 @@ class StreamKernel:
         w("  const long long task = (long long)blockIdx.x * NW + threadIdx.y;")
         w(f"  const int nk = {A}.g.k_hi - {A}.g.k_lo;")
         w("  if (task >= (long long)nseg * ntj * nk) return;")
-        w("  const int seg = (int)(task % nseg);")
-        w("  const int tj = (int)((task / nseg) % ntj);")
-        w(f"  const int k = {A}.g.k_lo + (int)(task / ((long long)nseg * ntj));")
+        halo_wait = bool(self.opts.get("halo_wait", False))
+        if halo_wait:
+            # multi-GPU J slabs with the peer-memory halo exchange: the first and the last J tile read rows the neighbours
+            # push into this rank's halo while this kernel is already running -> those tiles come LAST in the task order
+            # (all levels), behind every interior tile, so that by the time they start their halo has normally arrived
+            w("  int seg, tj, kk;")
+            w("  if (ntj >= 3) {")
+            w("    const long long n_int = (long long)nseg * (ntj - 2) * nk;   // interior tiles first")
+            w("    if (task < n_int) { seg = (int)(task % nseg); tj = 1 + (int)((task / nseg) % (ntj - 2)); kk = (int)(task / ((long long)nseg * (ntj - 2))); }")
+            w("    else { const long long tb = task - n_int; seg = (int)(tb % nseg); tj = ((tb / nseg) & 1) ? ntj - 1 : 0; kk = (int)(tb / (2LL * nseg)); }")
+            w("  } else { seg = (int)(task % nseg); tj = (int)((task / nseg) % ntj); kk = (int)(task / ((long long)nseg * ntj)); }")
+            w(f"  const int k = {A}.g.k_lo + kk;")
+        else:
+            w("  const int seg = (int)(task % nseg);")
+            w("  const int tj = (int)((task / nseg) % ntj);")
+            w(f"  const int k = {A}.g.k_lo + (int)(task / ((long long)nseg * ntj));")
         k0 = cg._bound(self.interval[0], f"{A}.g.nK")
         k1 = cg._bound(self.interval[1], f"{A}.g.nK")
         w(f"  if (k < {k0} || k >= {k1}) return;")
@@ -406,6 +421,20 @@ class StreamKernel:
         w("  const bool own = (lane >= HL) && (lane < HL + SQ);")
         w("  const int T_lo = Y0 + tj * TJ;")
         w("  const int T_hi = (T_lo + TJ < Y1) ? T_lo + TJ : Y1;")
+        if halo_wait:
+            ins_nj = [v.nj for v in self.values if v.kind == "in"]
+            lo_rows, hi_rows = min([0] + [n[0] for n in ins_nj]), max([0] + [n[1] for n in ins_nj])
+            w(f"  if ({A}.g.halo_epoch) {{   // tiles that read halo rows wait until the neighbour's rows of this step have landed")
+            w(f"    const bool need_lo = {A}.g.halo_flag_lo && (T_lo + ({lo_rows}) < 0);")
+            w(f"    const bool need_hi = {A}.g.halo_flag_hi && (T_hi + ({hi_rows}) > {A}.g.nJ);")
+            w("    if (need_lo || need_hi) {")
+            w("      if (lane == 0) {")
+            w(f"        if (need_lo) b200::wait_flag({A}.g.halo_flag_lo, {A}.g.halo_epoch);")
+            w(f"        if (need_hi) b200::wait_flag({A}.g.halo_flag_hi, {A}.g.halo_epoch);")
+            w("      }")
+            w("      __syncwarp();")
+            w("    }")
+            w("  }")
         for v in self.values:
             ct = CT[v.dtype]
             for s in range(v.window):

@@ -42,7 +42,14 @@ struct Geom {
   int j_lo, j_hi;    //   every stage additionally extends it by its own block extent
   int k_lo, k_hi;    // K range override for level-by-level launches (k_lo < 0: use the section intervals)
   int _pad;
+  // Multi-GPU J-slab runs with the peer-memory halo exchange (b200_halo_push): the neighbours store their boundary rows
+  // straight into this rank's halo rows over NVLink and then set these flags (in this rank's memory) to the step number.
+  // Kernels generated with `halo_wait` make the tiles that read halo rows wait for flag >= halo_epoch; 0 = no waiting.
+  unsigned long long* halo_flag_lo;
+  unsigned long long* halo_flag_hi;
+  unsigned long long halo_epoch;
 };
+static_assert(sizeof(Geom) == 64, "Geom layout (mirrored in launcher.cu, tests/emu/emu.py)");
 
 template <class T>
 __device__ __forceinline__ T ld(const T* p) {
@@ -147,6 +154,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TMap* tm, int c0, i
   if (!m.base) emu::fail("tensor map was not encoded");
   if (((uintptr_t)dst & 127) || ((uintptr_t)m.base & 15) || (m.stride[1] & 15) || (m.stride[2] & 15))
     emu::fail("cp.async.bulk.tensor: misaligned shared destination, global base or stride");
+  if (((uintptr_t)(m.base + (long long)c0 * m.isz)) & 15)
+    emu::fail("cp.async.bulk.tensor: the box must start on a 16-byte boundary along the unit-stride axis (illegal instruction on the device)");
   const unsigned bytes = (unsigned)(m.box[0] * m.box[1] * m.isz);
   if ((*bar >> 32) < bytes) emu::fail("cp.async.bulk.tensor: more bytes than the barrier expects");
   char* out = (char*)dst;
@@ -168,6 +177,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   __syncwarp();
 }
 #endif
+
+// wait until a peer has stored a value >= `epoch` into `*flag` (system-scope acquire: the halo rows the peer wrote before
+// the flag are visible afterwards).  Traps instead of hanging forever if the peer never arrives.
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long epoch) {
+#ifndef B200_HOST_EMU
+  unsigned long long v;
+  for (long long spin = 0;; ++spin) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= epoch) break;
+    __nanosleep(200);
+    if (spin > 20000000LL) __trap();  // ~ several seconds
+  }
+#else
+  if (*flag < epoch) emu::fail("halo flag wait would hang (the peer has not pushed this step)");
+#endif
+}
 
 __device__ __forceinline__ int clampk(long long k, int lo, int hi) {
   return (int)(k < lo ? lo : (k > hi - 1 ? hi - 1 : k));

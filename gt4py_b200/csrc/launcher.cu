@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
+#include <algorithm>
 #include <array>
 #include <map>
 #include <mutex>
@@ -60,9 +61,12 @@ struct Geom {
   int i_lo, i_hi, j_lo, j_hi;
   int k_lo, k_hi;
   int _pad;
+  unsigned long long* halo_flag_lo;
+  unsigned long long* halo_flag_hi;
+  unsigned long long halo_epoch;
 };
 static_assert(sizeof(FieldArg) == 80, "FieldArg layout");
-static_assert(sizeof(Geom) == 40, "Geom layout");
+static_assert(sizeof(Geom) == 64, "Geom layout");
 
 struct Bound {
   int level;  // 0 = START, 1 = END
@@ -432,6 +436,12 @@ const char* b200_stencil_kernel_name(const b200_stencil_t* st, int index) {
 
 int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
                      size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], void* stream_) {
+  return b200_stencil_run_halo(st, fields, nfields, scalars, scalars_size, domain, subbox, nullptr, nullptr, 0, stream_);
+}
+
+int b200_stencil_run_halo(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
+                          size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], uint64_t* flag_lo,
+                          uint64_t* flag_hi, uint64_t epoch, void* stream_) {
   if (!st || !domain) return fail(B200_ERR_INVALID, "b200_stencil_run: null argument");
   if (nfields != st->n_api)
     return fail(B200_ERR_INVALID, "stencil %s expects %d fields, got %d", st->name.c_str(), st->n_api, nfields);
@@ -492,6 +502,9 @@ int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields
   g->i_hi = subbox ? subbox[1] : domain[0];
   g->j_lo = subbox ? subbox[2] : 0;
   g->j_hi = subbox ? subbox[3] : domain[1];
+  g->halo_flag_lo = (unsigned long long*)flag_lo;
+  g->halo_flag_hi = (unsigned long long*)flag_hi;
+  g->halo_epoch = (flag_lo || flag_hi) ? epoch : 0;
   FieldArg* fa = reinterpret_cast<FieldArg*>(blob.data() + sizeof(Geom));
   int api = 0;
   for (size_t n = 0; n < nf; ++n) {
@@ -737,6 +750,34 @@ int nccl_load() {
     if (r_ != 0) return fail(B200_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));   \
   } while (0)
 
+// Peer-memory halo push (b200_halo_push): 16-byte lanes, one grid row per (level, row) of every box; the destination
+// is a peer GPU's memory mapped into this process (posted NVLink writes).
+struct PushArgs {
+  int n;
+  b200_push_t b[16];
+};
+struct FlagArgs {
+  int n;
+  unsigned long long* f[4];
+};
+template <class V>
+__global__ void halo_push_kernel(PushArgs a) {
+  const b200_push_t& b = a.b[blockIdx.z];
+  const size_t vecs = b.row_bytes / sizeof(V), total_rows = b.rows * b.levels;
+  for (size_t r = blockIdx.y; r < total_rows; r += gridDim.y) {
+    const size_t lev = r / b.rows, row = r % b.rows;
+    const V* s = reinterpret_cast<const V*>((const char*)b.src + lev * b.src_level_pitch + row * b.src_row_pitch);
+    V* d = reinterpret_cast<V*>((char*)b.dst + lev * b.dst_level_pitch + row * b.dst_row_pitch);
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < vecs; x += (size_t)gridDim.x * blockDim.x) d[x] = s[x];
+  }
+}
+__global__ void halo_flag_kernel(FlagArgs a, unsigned long long epoch) {
+  if (threadIdx.x < a.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.f[threadIdx.x]), "l"(epoch) : "memory");
+  }
+}
+
 // Re-layout of a 3-D array between two stride sets (storage.from_array: C-ordered upload -> pitched I-unit-stride
 // storage).  When the unit-stride axes differ the copy goes through a 32 x 32 shared-memory tile so that both the
 // reads and the writes are coalesced (a plain element-wise strided copy reaches ~0.4 TB/s, profiles/r01_launches_bench.csv).
@@ -790,6 +831,45 @@ int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
   return B200_OK;
 }
 
+// ---- peer-memory halo exchange: push my boundary rows into the neighbours' halo rows, then raise their flags -------
+int b200_halo_push(const b200_push_t* boxes, int nboxes, uint64_t* const* flags, int nflags, uint64_t epoch, void* stream_) {
+  if (nboxes < 0 || nflags < 0 || nboxes > 16 || nflags > 4 || (nboxes && !boxes) || (nflags && !flags))
+    return fail(B200_ERR_INVALID, "b200_halo_push: bad arguments");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PushArgs pa;
+  pa.n = nboxes;
+  unsigned max_rows = 1;
+  size_t max_bytes = 16, all = 0;  // OR of every address / size: the widest lane (16, 8 or 4 bytes) that divides them all
+  for (int n = 0; n < nboxes; ++n) {
+    const b200_push_t& b = boxes[n];
+    if (!b.src || !b.dst) return fail(B200_ERR_INVALID, "b200_halo_push: null box");
+    all |= (size_t)(uintptr_t)b.src | (size_t)(uintptr_t)b.dst | b.row_bytes | b.src_row_pitch | b.dst_row_pitch | b.src_level_pitch |
+           b.dst_level_pitch;
+    pa.b[n] = b;
+    max_bytes = std::max(max_bytes, b.row_bytes);
+    max_rows = std::max<unsigned>(max_rows, (unsigned)(b.rows * b.levels));
+  }
+  const int lane = (all & 15) == 0 ? 16 : ((all & 7) == 0 ? 8 : ((all & 3) == 0 ? 4 : 0));
+  if (nboxes && !lane) return fail(B200_ERR_INVALID, "b200_halo_push: rows must be multiples of 4 bytes at 4-byte aligned addresses");
+  if (nboxes) {
+    const unsigned chunks = (unsigned)std::min<size_t>((max_bytes / lane + 127) / 128, 64);
+    dim3 grid(chunks, std::min<unsigned>(max_rows, 65535u), (unsigned)nboxes);
+    if (lane == 16) halo_push_kernel<int4><<<grid, 128, 0, stream>>>(pa);
+    else if (lane == 8) halo_push_kernel<int2><<<grid, 128, 0, stream>>>(pa);
+    else halo_push_kernel<int><<<grid, 128, 0, stream>>>(pa);
+    CU(cudaGetLastError());
+  }
+  if (nflags) {
+    FlagArgs fa;
+    fa.n = nflags;
+    for (int n = 0; n < nflags; ++n) fa.f[n] = (unsigned long long*)flags[n];
+    // a second launch on the same stream: every byte of the push kernel has been written before this one starts
+    halo_flag_kernel<<<1, 32, 0, stream>>>(fa, epoch);
+    CU(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
 // ---- data movement helpers of the storage / host-call path -------------------------------------------------------
 int b200_copy_box(void* dst, size_t dst_pitch, size_t dst_level_rows, const void* src, size_t src_pitch,
                   size_t src_level_rows, size_t row_bytes, size_t rows, size_t levels, void* stream) {
@@ -812,11 +892,14 @@ int b200_relayout(void* dst, const void* src, int itemsize, const int32_t shape[
   for (int d = 0; d < 3; ++d)
     if (shape[d] <= 0) return B200_OK;
   // a = unit-stride axis of the destination, b = unit-stride axis of the source (fall back to the smallest stride)
-  int a = 0, b = 0;
-  for (int d = 1; d < 3; ++d) {
-    if (llabs(dst_strides[d]) < llabs(dst_strides[a]) || shape[a] == 1) a = d;
-    if (llabs(src_strides[d]) < llabs(src_strides[b]) || shape[b] == 1) b = d;
+  // (among the axes that have more than one element)
+  int a = -1, b = -1;
+  for (int d = 0; d < 3; ++d) {
+    if (shape[d] == 1) continue;
+    if (a < 0 || llabs(dst_strides[d]) < llabs(dst_strides[a])) a = d;
+    if (b < 0 || llabs(src_strides[d]) < llabs(src_strides[b])) b = d;
   }
+  if (a < 0) a = b = 0;  // a single element
   RelayoutArgs r;
   for (int d = 0; d < 3; ++d) {
     r.n[d] = shape[d];

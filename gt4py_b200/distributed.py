@@ -219,3 +219,135 @@ class HaloExchanger:
         if self._stream is not None:
             self._lib.b200_stream_destroy(self._stream)
             self._stream = None
+
+
+class PeerHalo:
+    """J-slab halo exchange over PEER MEMORY (NVLink / NVSwitch): no NCCL call, no staging, no pack / unpack kernels.
+
+    Every exchanged field lives in symmetric memory (`torch.distributed._symmetric_memory`: the same allocation made on
+    every rank and mapped into every process — plumbing).  Per step each rank runs ONE small kernel on its comm stream
+    (`b200_halo_push`, csrc/launcher.cu) that stores its boundary rows straight into the neighbours' halo rows and then
+    raises a flag in the neighbours' memory (system-scope release).  The consumer side is inside the stencil kernel:
+    kernels generated with `halo_wait=True` run the whole slab in ONE launch, order the two boundary J tiles last and let
+    them wait on the flags (device side, acquire) right before their first load — compute and exchange overlap tile by
+    tile, without boundary-strip launches or host-side event chains.
+
+    Ordering contract (one-step lag, two rotating buffer sets are enough): `push(fields)` must be enqueued after the
+    kernel that produced the rows it sends (the caller makes the comm stream wait for that) and the step that consumes
+    them must pass `wait_args()` of the same push."""
+
+    def __init__(self, decomp: SlabDecomposition, local_nj: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import runtime
+
+        self.decomp = decomp
+        self.local_nj = decomp.local_nj if local_nj is None else local_nj
+        self._torch, self._symm, self._lib = torch, symm, runtime.load_library()
+        self._group = group if group is not None else dist.group.WORLD
+        self._device = torch.device("cuda", torch.cuda.current_device())
+        self._handles: List[Any] = []
+        flags = symm.empty(8, dtype=torch.int64, device=self._device)  # [0] raised by rank-1, [1] by rank+1
+        flags.zero_()
+        torch.cuda.synchronize()
+        hdl = symm.rendezvous(flags, self._group)
+        self._flags, self._flag_ptrs = flags, [int(p) for p in hdl.buffer_ptrs]
+        self._handles.append(hdl)
+        hdl.barrier()
+        self.epoch = 0
+        s = ctypes.c_void_p()
+        runtime.check(self._lib.b200_stream_create_priority(ctypes.byref(s), 1))
+        self._stream = s
+        self._plans: Dict[Any, Any] = {}
+
+    @property
+    def stream(self) -> int:
+        return int(self._stream.value)
+
+    def _raw_alloc(self, nbytes: int):
+        return self._symm.empty(int(nbytes), dtype=self._torch.uint8, device=self._device)
+
+    def _register(self, arr):
+        """collective: rendezvous the allocation of `arr`; records where element [0,0,...] lives on every rank"""
+        import torch.distributed as dist
+
+        hdl = self._symm.rendezvous(arr._raw, self._group)
+        self._handles.append(hdl)
+        off = int(arr.data_ptr) - int(arr._raw.data_ptr())
+        offs = [None] * self.decomp.n_ranks
+        dist.all_gather_object(offs, off, group=self._group)
+        arr._peer_ptrs = [int(p) + int(o) for p, o in zip(hdl.buffer_ptrs, offs)]
+        return arr
+
+    def empty(self, shape, dtype=np.float32, *, aligned_index=None, dimensions=None, fill=None):
+        """Collective (every rank, same order, same arguments): a b200 storage in symmetric memory."""
+        from . import storage as b2storage
+
+        return self._register(b2storage.empty(shape, dtype, aligned_index=aligned_index, dimensions=dimensions, _fill=fill, raw_alloc=self._raw_alloc))
+
+    def from_array(self, data, *, aligned_index=None, dimensions=None):
+        from . import storage as b2storage
+
+        return self._register(b2storage.from_array(data, aligned_index=aligned_index, dimensions=dimensions, raw_alloc=self._raw_alloc))
+
+    def _plan(self, fields):
+        from . import runtime
+
+        key = tuple((int(a.data_ptr), oj, h) for a, oj, h in fields)
+        plan = self._plans.get(key)
+        if plan is not None:
+            return plan
+        d, nj = self.decomp, self.local_nj
+        boxes = []
+        for arr, oj, h in fields:
+            if not hasattr(arr, "_peer_ptrs"):
+                raise ValueError("PeerHalo: the field was not allocated with PeerHalo.empty / from_array")
+            si, sj, sk = arr.element_strides
+            item = arr.itemsize
+            if si != 1 or arr.ndim != 3:
+                raise ValueError("PeerHalo: fields must be 3-D and I-contiguous")
+            nrow = ((h - 1) * sj + arr.shape[0]) * item  # h consecutive logical rows incl. the padding between them
+            for peer, send_j, recv_j in ((d.peer_lo, oj, oj + nj), (d.peer_hi, oj + nj - h, oj - h)):
+                if peer < 0:
+                    continue
+                b = runtime.B200Push()
+                b.src = int(arr.data_ptr) + send_j * sj * item
+                b.dst = arr._peer_ptrs[peer] + recv_j * sj * item
+                b.row_bytes, b.rows, b.levels = nrow, 1, arr.shape[2]
+                b.src_row_pitch = b.dst_row_pitch = sj * item
+                b.src_level_pitch = b.dst_level_pitch = sk * item
+                boxes.append(b)
+        flags = []
+        if d.peer_lo >= 0:
+            flags.append(self._flag_ptrs[d.peer_lo] + 8)  # I am the lower neighbour's rank+1
+        if d.peer_hi >= 0:
+            flags.append(self._flag_ptrs[d.peer_hi] + 0)  # I am the upper neighbour's rank-1
+        plan = ((runtime.B200Push * max(1, len(boxes)))(*boxes), len(boxes), (ctypes.c_void_p * max(1, len(flags)))(*flags), len(flags))
+        self._plans[key] = plan
+        return plan
+
+    def push(self, fields: Sequence[Tuple[Any, int, int]], *, stream: Optional[int] = None) -> int:
+        """Enqueue the push of the boundary rows of `fields` [(array, origin_j, halo width)] + the flag stores on `stream`
+        (default: the exchanger's high-priority stream).  Returns the number of kernels launched."""
+        from . import runtime
+
+        boxes, nb, flags, nf = self._plan(fields)
+        self.epoch += 1
+        runtime.check(self._lib.b200_halo_push(boxes, nb, flags, nf, self.epoch, ctypes.c_void_p(self.stream if stream is None else stream)))
+        return (1 if nb else 0) + (1 if nf else 0)
+
+    def wait_args(self) -> Tuple[int, int, int]:
+        """(flag_lo, flag_hi, epoch) for `FrozenStencil(..., halo_wait=...)` / b200_stencil_run_halo of the step that
+        consumes the rows of the latest push."""
+        me = self._flag_ptrs[self.decomp.rank]
+        return (me if self.decomp.peer_lo >= 0 else 0, me + 8 if self.decomp.peer_hi >= 0 else 0, self.epoch)
+
+    def barrier(self):
+        self._handles[0].barrier()
+
+    def close(self):
+        if self._stream is not None:
+            self._lib.b200_stream_destroy(self._stream)
+            self._stream = None

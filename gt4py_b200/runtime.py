@@ -27,12 +27,23 @@ LIB_PATH = _PKG / "libgt4py_b200.so"
 EXPORTED_SYMBOLS = (
     "b200_abi_version", "b200_sizeof_field", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
     "b200_stencil_num_fields", "b200_stencil_scalars_size", "b200_stencil_num_kernels", "b200_stencil_kernel_name",
-    "b200_stencil_run", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
+    "b200_stencil_run", "b200_stencil_run_halo", "b200_halo_push", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
     "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
     "b200_halo_exchange", "b200_pack_2d", "b200_copy_box", "b200_relayout",
     "b200_graph_begin", "b200_graph_end", "b200_graph_num_nodes", "b200_graph_launch", "b200_graph_destroy",
 )  # fmt: skip
+
+
+class B200Push(ctypes.Structure):
+    """b200_push_t (include/gt4py_b200.h): one box of rows pushed into a neighbour's memory"""
+
+    _fields_ = [
+        ("src", ctypes.c_void_p), ("dst", ctypes.c_void_p),
+        ("row_bytes", ctypes.c_size_t), ("rows", ctypes.c_size_t), ("levels", ctypes.c_size_t),
+        ("src_row_pitch", ctypes.c_size_t), ("src_level_pitch", ctypes.c_size_t),
+        ("dst_row_pitch", ctypes.c_size_t), ("dst_level_pitch", ctypes.c_size_t),
+    ]  # fmt: skip
 
 
 class B200Field(ctypes.Structure):
@@ -90,6 +101,9 @@ def load_library(build_if_missing: bool = True):
             "b200_stencil_num_kernels": (ci, [vp]),
             "b200_stencil_kernel_name": (ctypes.c_char_p, [vp, ci]),
             "b200_stencil_run": (ci, [vp, ctypes.POINTER(B200Field), ci, vp, cz, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), vp]),
+            "b200_stencil_run_halo": (ci, [vp, ctypes.POINTER(B200Field), ci, vp, cz, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                          vp, vp, ctypes.c_uint64, vp]),
+            "b200_halo_push": (ci, [ctypes.POINTER(B200Push), ci, ctypes.POINTER(ctypes.c_void_p), ci, ctypes.c_uint64, vp]),
             "b200_stream_create": (ci, [pvp]),
             "b200_stream_create_priority": (ci, [pvp, ci]),
             "b200_stream_destroy": (ci, [vp]),
@@ -417,10 +431,11 @@ class CompiledStencil:
             self._special[pitch] = cs
         return cs
 
-    def run_descs(self, descs, scalars: bytes, domain, *, stream=None, subbox=None) -> int:
+    def run_descs(self, descs, scalars: bytes, domain, *, stream=None, subbox=None, halo_wait=None) -> int:
+        """halo_wait = (flag_lo address or 0, flag_hi address or 0, epoch): see b200_stencil_run_halo"""
         target = self.specialized_for(descs)
         if target is not self:
-            n = target.run_descs(descs, scalars, domain, stream=stream, subbox=subbox)
+            n = target.run_descs(descs, scalars, domain, stream=stream, subbox=subbox, halo_wait=halo_wait)
             self.last_launches = n
             return n
         lib = load_library()
@@ -438,7 +453,12 @@ class CompiledStencil:
                 sb = self._dom_cache[bkey] = (ctypes.c_int32 * 4)(*[int(x) for x in subbox])
         if stream is None:
             stream = current_stream_handle()
-        n = check(lib.b200_stencil_run(self.handle, descs, len(self._api), scalars, len(scalars), dom, sb, ctypes.c_void_p(stream)))
+        if halo_wait is not None:
+            flo, fhi, epoch = halo_wait
+            n = check(lib.b200_stencil_run_halo(self.handle, descs, len(self._api), scalars, len(scalars), dom, sb,
+                                                ctypes.c_void_p(flo or None), ctypes.c_void_p(fhi or None), int(epoch), ctypes.c_void_p(stream)))  # fmt: skip
+        else:
+            n = check(lib.b200_stencil_run(self.handle, descs, len(self._api), scalars, len(scalars), dom, sb, ctypes.c_void_p(stream)))
         self.last_launches = n
         return n
 

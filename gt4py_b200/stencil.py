@@ -580,7 +580,7 @@ class FrozenStencil:
         self._cache[ids] = (descs, args, tuple((_ptr_of(a), getattr(a, "shape", None)) for a in args))
         return descs
 
-    def __call__(self, *, exec_info=None, stream=None, subbox=None, **kwargs) -> int:
+    def __call__(self, *, exec_info=None, stream=None, subbox=None, halo_wait=None, **kwargs) -> int:
         st = self.stencil_object
         descs = self._descs_for(kwargs)
         if self._pnames:
@@ -590,7 +590,7 @@ class FrozenStencil:
                 self._scal_key = skey
         elif self._scal is None:
             self._scal = st.compiled.pack_scalars({})
-        n = st.compiled.run_descs(descs, self._scal, self.domain, stream=stream, subbox=subbox)
+        n = st.compiled.run_descs(descs, self._scal, self.domain, stream=stream, subbox=subbox, halo_wait=halo_wait)
         if st.device_sync:
             runtime.check(runtime.load_library().b200_stream_synchronize(stream if stream is not None else runtime.current_stream_handle()))
         return n

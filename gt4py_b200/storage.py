@@ -472,28 +472,31 @@ def _device(device=None):
     return torch.device("cuda", torch.cuda.current_device() if device is None else device)
 
 
-def allocate(shape, lmap, dtype, alignment_elems: int, aligned_index, *, device=None, fill=None) -> DeviceArray:
+def allocate(shape, lmap, dtype, alignment_elems: int, aligned_index, *, device=None, fill=None, raw_alloc=None) -> DeviceArray:
+    """raw_alloc(nbytes) -> 1-D uint8 device tensor: where the bytes come from (default: torch's caching allocator;
+    distributed.PeerHalo passes a symmetric-memory allocator so that neighbour ranks can address the storage)."""
     torch = _torch()
     dtype = np.dtype(dtype)
     estrides, total, lead = compute_layout(shape, lmap, dtype.itemsize, alignment_elems, aligned_index)
     align_bytes = max(alignment_elems * dtype.itemsize, 256)
     nbytes = (total + lead) * dtype.itemsize + align_bytes
-    raw = torch.empty(nbytes, dtype=torch.uint8, device=_device(device))
+    raw = raw_alloc(nbytes) if raw_alloc is not None else torch.empty(nbytes, dtype=torch.uint8, device=_device(device))
     mis = (-raw.data_ptr()) % align_bytes
     end = mis + (total + lead) * dtype.itemsize
     base = raw[mis:end].view(_torch_dtype(dtype))
     arr = DeviceArray(base, lead, shape, estrides, dtype)
+    arr._raw = raw  # the allocation itself (symmetric-memory rendezvous needs the tensor the allocator returned)
     if fill is not None:
         base.fill_(fill)
     return arr
 
 
 # ---- public constructors (reference: storage/cartesian/interface.py:40-327) --------------------
-def empty(shape, dtype=np.float64, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None, _fill=None):
+def empty(shape, dtype=np.float64, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None, _fill=None, raw_alloc=None):
     if backend != "b200":
         raise RuntimeError(f"Storage preset '{backend}' is not handled by gt4py_b200.storage.")
     aligned_index, shape, dtype, dimensions = normalize_storage_spec(aligned_index, shape, dtype, dimensions)
-    return allocate(shape, layout_map(dimensions), dtype, ALIGNMENT_ELEMENTS, aligned_index, device=device, fill=_fill)
+    return allocate(shape, layout_map(dimensions), dtype, ALIGNMENT_ELEMENTS, aligned_index, device=device, fill=_fill, raw_alloc=raw_alloc)
 
 
 def zeros(shape, dtype=np.float64, **kwargs):
@@ -508,7 +511,7 @@ def full(shape, fill_value, dtype=np.float64, **kwargs):
     return empty(shape, dtype, _fill=fill_value, **kwargs)
 
 
-def from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None):
+def from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, dimensions=None, device=None, raw_alloc=None):
     src = data.get() if isinstance(data, DeviceArray) else np.asarray(data)
     shape = src.shape
     if dtype is None:
@@ -518,7 +521,7 @@ def from_array(data, dtype=None, *, backend: str = "b200", aligned_index=None, d
         if shape[-dtype.ndim :] != dtype.shape:
             raise ValueError(f"Incompatible data shape {shape} with dtype of shape {dtype.shape}.")
         shape = shape[: -dtype.ndim]
-    out = empty(shape, dtype, backend=backend, aligned_index=aligned_index, dimensions=dimensions, device=device)
+    out = empty(shape, dtype, backend=backend, aligned_index=aligned_index, dimensions=dimensions, device=device, raw_alloc=raw_alloc)
     out[...] = src.astype(out.dtype, copy=False)
     return out
 

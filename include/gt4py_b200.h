@@ -81,6 +81,13 @@ const char* b200_stencil_kernel_name(const b200_stencil_t* st, int index);
 int b200_stencil_run(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
                      size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], void* stream);
 
+/* The same call for a rank of a J-slab decomposition whose halo rows are written by the neighbours' b200_halo_push:
+ * kernels generated with the `halo_wait` option make the tiles that read halo rows wait (on the device) until
+ * *flag_lo / *flag_hi >= epoch before their first load.  A NULL flag = no neighbour on that side. */
+int b200_stencil_run_halo(b200_stencil_t* st, const b200_field_t* fields, int nfields, const void* scalars,
+                          size_t scalars_size, const int32_t domain[3], const int32_t subbox[4], uint64_t* flag_lo,
+                          uint64_t* flag_hi, uint64_t epoch, void* stream);
+
 /* ---- streams / events (device-side timing for exec_info and bench) --------------------------- */
 int b200_stream_create(void** stream);
 /* non-blocking stream with the highest (high != 0) or lowest scheduling priority of the device: halo exchange and
@@ -124,6 +131,17 @@ typedef struct b200_halo {
   size_t bytes;
 } b200_halo_t;
 int b200_halo_exchange(b200_comm_t* comm, const b200_halo_t* halos, int n_halos, int peer_lo, int peer_hi, void* stream);
+/* Halo exchange over PEER MEMORY (NVLink / NVSwitch, no NCCL call, no staging): copy `nboxes` boxes of rows from this
+ * rank's memory into the neighbours' memory (`dst` = address of the neighbour's halo rows mapped into this process,
+ * e.g. torch symmetric memory), then store `epoch` to each of `flags` (also in the neighbours' memory) with system-scope
+ * release semantics.  The neighbour consumes the rows with b200_stencil_run_halo.  Everything is enqueued on `stream`. */
+typedef struct b200_push {
+  const void* src; void* dst;
+  size_t row_bytes, rows, levels;                 /* per box: levels x rows rows of row_bytes bytes (4-byte multiples) */
+  size_t src_row_pitch, src_level_pitch;          /* bytes */
+  size_t dst_row_pitch, dst_level_pitch;
+} b200_push_t;
+int b200_halo_push(const b200_push_t* boxes, int nboxes, uint64_t* const* flags, int nflags, uint64_t epoch, void* stream);
 /* Strided slab <-> contiguous staging buffer copy kernels (J-halo slabs of a (2,1,0)-layout field
  * are nK separate chunks): rows × row_bytes, source/destination pitch in bytes. */
 int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);

@@ -98,7 +98,7 @@ class EmuStencil:
         origin = [lead if dims[0] else 0, -ej0 if dims[1] else 0, 0]
         return s, origin, vol * nd, nk
 
-    def run(self, fields, params, domain, origins, subbox=None, layout=None, guard=None):
+    def run(self, fields, params, domain, origins, subbox=None, layout=None, guard=None, halo_wait=(0, 0, 0)):
         """fields: name -> numpy arrays in IJK[+data] axis order (modified in place).
 
         layout="b200": stage every field in the backend's storage layout first (I unit-stride, rows
@@ -114,7 +114,7 @@ class EmuStencil:
                     staged[name] = None
                     continue
                 staged[name] = _stage_b200(arr, origins[name], guard, keep)
-            self.run(staged, params, domain, origins, subbox=subbox)
+            self.run(staged, params, domain, origins, subbox=subbox, halo_wait=halo_wait)
             for name, arr in fields.items():
                 if arr is not None:
                     arr[...] = staged[name]
@@ -178,7 +178,7 @@ class EmuStencil:
         i_lo, i_hi, j_lo, j_hi = subbox if subbox is not None else (0, dom[0], 0, dom[1])
 
         def blob(k_lo, k_hi):
-            b = struct.pack("<10i", dom[0], dom[1], dom[2], i_lo, i_hi, j_lo, j_hi, k_lo, k_hi, 0)
+            b = struct.pack("<10i3Q", dom[0], dom[1], dom[2], i_lo, i_hi, j_lo, j_hi, k_lo, k_hi, 0, *halo_wait)  # Geom (64 bytes)
             for ptr, s, klo, khi, vec in (fa if fa else [(0, [0] * 7, 0, 0, 0)]):
                 b += struct.pack("<Q7q4i", ptr, *s, klo, khi, vec, 0)
             b += scal

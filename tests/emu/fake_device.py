@@ -110,7 +110,7 @@ def install(mp) -> None:
 
     capture = {"on": False, "calls": [], "graphs": {}}
 
-    def run_descs(self, descs, scalars, domain, *, stream=None, subbox=None):
+    def run_descs(self, descs, scalars, domain, *, stream=None, subbox=None, halo_wait=None):
         if capture["on"]:  # CUDA-graph capture: nothing executes, the launches are recorded with frozen arguments
             frozen_descs = type(descs).from_buffer_copy(descs)
             capture["calls"].append((self, frozen_descs, bytes(scalars), tuple(domain), None if subbox is None else tuple(subbox)))
@@ -132,7 +132,8 @@ def install(mp) -> None:
         params = {s["name"]: v for s, v in zip(target._scalars, vals)}
         target._emu_domain = tuple(int(x) for x in domain)
         before = emu.launches
-        emu.run(fields, params, tuple(int(x) for x in domain), origins, subbox=tuple(subbox) if subbox is not None else None)
+        emu.run(fields, params, tuple(int(x) for x in domain), origins, subbox=tuple(subbox) if subbox is not None else None,
+                halo_wait=tuple(int(x or 0) for x in halo_wait) if halo_wait is not None else (0, 0, 0))
         self.last_launches = emu.launches - before
         return self.last_launches
 

@@ -97,7 +97,7 @@ def test_autotune_control_flow_with_a_stubbed_device(monkeypatch):
     fields = {"in_field": dev(1.0), "coeff": dev(0.5), "out_field": dev(0.0)}
     calls = []
 
-    def fake_run(self, descs, scalars, domain, *, stream=None, subbox=None):
+    def fake_run(self, descs, scalars, domain, *, stream=None, subbox=None, halo_wait=None):
         calls.append(dict(self.options))
         bad = self.options.get("tile_j") == 32  # this variant "computes" something else
         fields["out_field"].torch().fill_(7.0 if not bad else 8.0)

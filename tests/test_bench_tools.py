@@ -37,5 +37,7 @@ def test_reference_arm_prints_one_json_line():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)  # fmt: skip
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    # the reference's own numpy backend where the reference package is importable (baseline/_ref or /root/reference), else the port
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert "1024x1024x80" in line["config"]["workload"] and "whole 1024x1024x80" in line["cpu_baseline"]["sample"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "Mcell-updates/s"

@@ -271,7 +271,7 @@ def test_in_place_update_through_a_temporary_on_a_multi_tile_domain(options):
 
 def test_parallel_sections_coupled_through_a_k_offset_are_separate_ordered_launches():
     """ADVICE r1 (medium): one kernel for all sections of a PARALLEL loop runs them concurrently (K on blockIdx.z);
-    `interval(0,2): b = a*2; interval(2,None): c = b[0,0,-2] + 1` (one vertical loop after AdjacentLoopMerging) needs
+    `interval(0,1): b = a*2; interval(1,None): c = b[0,0,-1] + 1` (one vertical loop after AdjacentLoopMerging) needs
     the first section finished before the second starts."""
     for variant in ("default", "staged"):
         st = testing.load_ir("sections_koff_f64", variant)
@@ -283,3 +283,25 @@ def test_parallel_sections_coupled_through_a_k_offset_are_separate_ordered_launc
     # independent sections still share one kernel
     es = run_emulated("k_intervals_f64", "default", {"strategy": "point"})
     assert len([s for s in es.plan["steps"] if s["t"] == "launch"]) == 1
+
+
+def test_halo_wait_kernels_put_the_boundary_tiles_last_and_wait_for_the_flags():
+    """multi-GPU variant of the streaming kernel (`halo_wait`): same results as the plain kernel; the tiles that read halo
+    rows are the last tasks of the grid and wait for the neighbours' flags (Geom::halo_flag_*, b200_stencil_run_halo)"""
+    import ctypes
+
+    st = testing.load_ir("hdiff_f32", "staged")
+    domain = (150, 260, 3)  # 5 J tiles of 64 rows
+    fields, params, origins, domain = testing.make_case_data(st, "hdiff_f32", domain=domain, seed=4)
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    flags = (ctypes.c_uint64 * 2)(7, 7)
+    addr = ctypes.addressof(flags)
+    for opts in ({"halo_wait": True}, {"halo_wait": True, "interior_loop": True, "static_pitch": 160}):
+        es = EmuStencil(st, opts, name="hdiff_halo_wait")
+        assert "wait_flag" in es.source and "interior tiles first" in es.source
+        for hw in ((0, 0, 0), (addr, addr + 8, 7), (addr, 0, 5)):
+            got = {k: v.copy() for k, v in fields.items()}
+            es.run(got, params, domain, origins, layout="b200", guard="end", halo_wait=hw)
+            np.testing.assert_array_equal(got["out_field"], ref["out_field"])
+    assert "wait_flag" not in EmuStencil(st, {}, name="hdiff_plain").source

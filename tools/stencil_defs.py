@@ -701,7 +701,7 @@ def sections_koff_f64(a: F64, b: F64, c: F64):
     # adjacent-interval PARALLEL computations are merged into ONE vertical loop by the reference
     # (AdjacentLoopMerging); the second section reads at a K offset what the first one writes
     with computation(PARALLEL):
-        with interval(0, 2):
+        with interval(0, 1):
             b = a * 2.0
-        with interval(2, None):
-            c = b[0, 0, -2] + 1.0
+        with interval(1, None):
+            c = b[0, 0, -1] + 1.0
