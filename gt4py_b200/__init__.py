@@ -19,6 +19,21 @@ Layout of the package (only what the hot path needs):
 
 __version__ = "0.1.0"
 
+def register() -> bool:
+    """Register `backend="b200"` with gt4py now (for processes that made gt4py importable only after importing this
+    package).  True when the plug-in is registered."""
+    global HAVE_GT4PY
+    try:
+        import gt4py.cartesian  # noqa: F401
+
+        from . import backend as _backend  # noqa: F401
+
+        HAVE_GT4PY = True
+    except ImportError:
+        HAVE_GT4PY = False
+    return HAVE_GT4PY
+
+
 try:  # register backend="b200" with gt4py when the frontend is available
     import gt4py.cartesian  # noqa: F401
 

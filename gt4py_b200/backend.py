@@ -195,6 +195,7 @@ def get_compiled(ir_path: str, options_json: str) -> runtime.CompiledStencil:
                 cs.save(path.parent, path.stem)
             except OSError:
                 pass  # read-only cache directory: keep the in-memory build
+        cs._persist = (path.parent, path.stem)  # lazily specialised variants live next to the module as well
         _COMPILED[key] = cs
     return cs
 

@@ -771,6 +771,21 @@ __global__ void halo_push_kernel(PushArgs a) {
     for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < vecs; x += (size_t)gridDim.x * blockDim.x) d[x] = s[x];
   }
 }
+// consumer side for stencils whose kernels cannot wait themselves (point / column kernels): one thread spins on this
+// rank's flags; the stencil launched behind it on the same stream starts once the neighbours' rows have landed
+__global__ void halo_wait_kernel(const unsigned long long* lo, const unsigned long long* hi, unsigned long long epoch) {
+  const unsigned long long* f[2] = {lo, hi};
+  for (int n = 0; n < 2; ++n) {
+    if (!f[n]) continue;
+    unsigned long long v;
+    for (long long spin = 0;; ++spin) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f[n]) : "memory");
+      if (v >= epoch) break;
+      __nanosleep(200);
+      if (spin > 20000000LL) __trap();
+    }
+  }
+}
 __global__ void halo_flag_kernel(FlagArgs a, unsigned long long epoch) {
   if (threadIdx.x < a.n) {
     __threadfence_system();
@@ -867,6 +882,13 @@ int b200_halo_push(const b200_push_t* boxes, int nboxes, uint64_t* const* flags,
     halo_flag_kernel<<<1, 32, 0, stream>>>(fa, epoch);
     CU(cudaGetLastError());
   }
+  return B200_OK;
+}
+
+int b200_halo_wait(const uint64_t* flag_lo, const uint64_t* flag_hi, uint64_t epoch, void* stream) {
+  if (!flag_lo && !flag_hi) return B200_OK;
+  halo_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)flag_lo, (const unsigned long long*)flag_hi, epoch);
+  CU(cudaGetLastError());
   return B200_OK;
 }
 

@@ -344,6 +344,17 @@ class PeerHalo:
         me = self._flag_ptrs[self.decomp.rank]
         return (me if self.decomp.peer_lo >= 0 else 0, me + 8 if self.decomp.peer_hi >= 0 else 0, self.epoch)
 
+    def wait(self, stream: int) -> int:
+        """Consumer side for stencils without `halo_wait` kernels: a one-thread kernel on `stream` that returns when the
+        rows of the latest push have landed (b200_halo_wait).  Returns the number of kernels launched."""
+        from . import runtime
+
+        lo, hi, epoch = self.wait_args()
+        if not (lo or hi):
+            return 0
+        runtime.check(self._lib.b200_halo_wait(ctypes.c_void_p(lo or None), ctypes.c_void_p(hi or None), int(epoch), ctypes.c_void_p(stream)))
+        return 1
+
     def barrier(self):
         self._handles[0].barrier()
 

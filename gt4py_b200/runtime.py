@@ -27,7 +27,7 @@ LIB_PATH = _PKG / "libgt4py_b200.so"
 EXPORTED_SYMBOLS = (
     "b200_abi_version", "b200_sizeof_field", "b200_last_error", "b200_device_info", "b200_stencil_load", "b200_stencil_unload",
     "b200_stencil_num_fields", "b200_stencil_scalars_size", "b200_stencil_num_kernels", "b200_stencil_kernel_name",
-    "b200_stencil_run", "b200_stencil_run_halo", "b200_halo_push", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
+    "b200_stencil_run", "b200_stencil_run_halo", "b200_halo_push", "b200_halo_wait", "b200_stream_create", "b200_stream_create_priority", "b200_stream_destroy", "b200_stream_synchronize",
     "b200_event_create", "b200_event_destroy", "b200_event_record", "b200_stream_wait_event",
     "b200_event_elapsed_ms", "b200_comm_unique_id", "b200_comm_init", "b200_comm_destroy",
     "b200_halo_exchange", "b200_pack_2d", "b200_copy_box", "b200_relayout",
@@ -104,6 +104,7 @@ def load_library(build_if_missing: bool = True):
             "b200_stencil_run_halo": (ci, [vp, ctypes.POINTER(B200Field), ci, vp, cz, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                           vp, vp, ctypes.c_uint64, vp]),
             "b200_halo_push": (ci, [ctypes.POINTER(B200Push), ci, ctypes.POINTER(ctypes.c_void_p), ci, ctypes.c_uint64, vp]),
+            "b200_halo_wait": (ci, [vp, vp, ctypes.c_uint64, vp]),
             "b200_stream_create": (ci, [pvp]),
             "b200_stream_create_priority": (ci, [pvp, ci]),
             "b200_stream_destroy": (ci, [vp]),
@@ -265,6 +266,14 @@ def set_stream_override(handle: Optional[int]) -> None:
     _stream_override.handle = handle
 
 
+#: what `specialize="lazy"` adds to the options at the first call with a given row pitch (besides `static_pitch`):
+#: the winners of the device sweeps (profiles/README.md, r02): interior warps without per-lane predicates
+LAZY_VARIANT: Dict[str, Any] = {"interior_loop": True}
+#: default of the `specialize` option ("lazy" | "off"); GT4PY_B200_SPECIALIZE overrides it (the test-suites pin "off"
+#: where they count kernels / compilations)
+DEFAULT_SPECIALIZE = "lazy"
+
+
 # ---- compiled stencil -----------------------------------------------------------------------------
 class CompiledStencil:
     """Generated CUDA code + launch plan of one stencil, loaded lazily into the launcher."""
@@ -285,8 +294,9 @@ class CompiledStencil:
         # specialize="lazy": at the first call with a given row pitch, compile (once, disk-cached) the
         # variant of the streaming kernels with that pitch as a compile-time constant + the interior
         # steady loop (codegen_stream.py) and use it for every later call with the same pitch
-        self._specialize = str(self.options.get("specialize", "off"))
+        self._specialize = str(self.options.get("specialize", os.environ.get("GT4PY_B200_SPECIALIZE", DEFAULT_SPECIALIZE)))
         self._special: Dict[int, "CompiledStencil"] = {}
+        self._persist: Optional[Tuple[Any, str]] = None  # (.gt_cache directory, stem): where specialisations are kept too
         self._handle = None
         self._api = [f for f in self.plan["fields"] if f["kind"] == "api"]
         self._scalars = self.plan["scalars"]
@@ -426,8 +436,19 @@ class CompiledStencil:
         pitch = pitches.pop()
         cs = self._special.get(pitch)
         if cs is None:
-            opts = {**self.options, "static_pitch": pitch, "interior_loop": True, "specialize": "off"}
-            cs = CompiledStencil(self.ir, opts, name=self.name)
+            opts = {**LAZY_VARIANT, **self.options, "static_pitch": pitch, "specialize": "off"}
+            if self._persist is not None:  # warm start: the specialised cubin of an earlier process
+                cs = CompiledStencil.load(self.ir, opts, self._persist[0], f"{self._persist[1]}.p{pitch}", name=self.name)
+            if cs is None:
+                try:
+                    cs = CompiledStencil(self.ir, opts, name=self.name)
+                except Exception:  # a variant that does not apply to this stencil: keep the generic kernels
+                    cs = self
+                if cs is not self and self._persist is not None:
+                    try:
+                        cs.save(self._persist[0], f"{self._persist[1]}.p{pitch}")
+                    except OSError:
+                        pass
             self._special[pitch] = cs
         return cs
 

@@ -358,6 +358,21 @@ class B200Stencil:
         {"interior_loop": True, "static_pitch": "auto", "min_blocks": 8, "tile_j": 128},
         {"interior_loop": True, "static_pitch": "auto", "min_blocks": 9},
         {"interior_loop": True, "static_pitch": "auto", "tile_j": 256},
+        # bulk-async variants (codegen_stream.py: tensor-map copies into a per-warp shared-memory ring, LDS reads)
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "tile_j": 32, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 48, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 24, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 16, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "tile_j": 48, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "warps": 2},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "l2_prefetch": 4},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "stcs": True},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "tma_rows": 8, "tma_smem_kb": 48},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "warps": 2},
         {"edge_loop": True},
         {"pure_loop": False},
         {"vector_width": 4},
@@ -412,6 +427,7 @@ class B200Stencil:
             opts = {**base, **cand}
             try:
                 cs = runtime.CompiledStencil(self.ir, opts, name=self.name)
+                cs._specialize = "off"  # candidates are explicit variants: no lazy re-specialisation on top of them
             except Exception:  # a variant that does not apply to this stencil
                 continue
             if cs.source in seen:

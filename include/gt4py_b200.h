@@ -142,6 +142,9 @@ typedef struct b200_push {
   size_t dst_row_pitch, dst_level_pitch;
 } b200_push_t;
 int b200_halo_push(const b200_push_t* boxes, int nboxes, uint64_t* const* flags, int nflags, uint64_t epoch, void* stream);
+/* Consumer side for stencils whose kernels were not generated with `halo_wait`: enqueue a one-thread kernel on `stream`
+ * that returns once *flag_lo / *flag_hi (this rank's memory, NULL = no neighbour) have reached `epoch`. */
+int b200_halo_wait(const uint64_t* flag_lo, const uint64_t* flag_hi, uint64_t epoch, void* stream);
 /* Strided slab <-> contiguous staging buffer copy kernels (J-halo slabs of a (2,1,0)-layout field
  * are nK separate chunks): rows × row_bytes, source/destination pitch in bytes. */
 int b200_pack_2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows, void* stream);

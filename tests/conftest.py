@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# `specialize="lazy"` is the backend's default (a second, per-pitch cubin at the first call): the suites pin "off" so that
+# tests which count kernels / compilations see the generic kernels unless they ask for the specialisation themselves
+__import__("os").environ.setdefault("GT4PY_B200_SPECIALIZE", "off")
+
 ROOT = pathlib.Path(__file__).resolve().parent.parent
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

@@ -52,7 +52,7 @@ def test_bad_plan_is_rejected():
     assert rc < 0 and b"plan" in lib.b200_last_error()
 
 
-def test_lazy_pitch_specialisation_selects_one_variant_per_pitch():
+def test_lazy_pitch_specialisation_selects_one_variant_per_pitch(monkeypatch):
     """specialize="lazy": descriptors with a common unit-stride row pitch get the static-pitch +
     interior-loop variant of the streaming kernels (compiled once per pitch); anything else keeps
     the generic kernels.  Code generation + nvcc only — nothing is launched here."""
@@ -72,7 +72,11 @@ def test_lazy_pitch_specialisation_selects_one_variant_per_pitch():
     assert cs.specialized_for(descs(64)) is a  # cached
     assert cs.specialized_for(descs(96)).options["static_pitch"] == 96
     assert cs.specialized_for(descs(64, si=2)) is cs  # not I-contiguous: generic kernels
-    assert runtime.CompiledStencil(st, {}).specialized_for(descs(64)).options.get("static_pitch") is None
+    assert runtime.CompiledStencil(st, {"specialize": "off"}).specialized_for(descs(64)).options.get("static_pitch") is None
+    # the backend's default is "lazy" (the suites pin GT4PY_B200_SPECIALIZE=off, tests/conftest.py)
+    monkeypatch.delenv("GT4PY_B200_SPECIALIZE", raising=False)
+    dflt = runtime.CompiledStencil(st, {}).specialized_for(descs(64))
+    assert dflt.options["static_pitch"] == 64 and dflt.options["interior_loop"] is True
     col = runtime.CompiledStencil(testing.load_ir("tridiagonal_f64"), {"specialize": "lazy"})
     assert not col._special and all(k["kind"] != "stream" for k in col.plan["kernels"])
 

@@ -156,6 +156,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", required=True, choices=["tridiagonal", "upwind5", "fastwaves", "hdiff_x2"])
     ap.add_argument("--fuse", action="store_true", help="run the stencils of a step as one fused stencil (gt4py_b200/fuse.py)")
+    ap.add_argument("--peer", action="store_true", help="N>1: peer-memory halo exchange (symmetric memory pushes) instead of NCCL SendRecv")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
@@ -173,7 +174,7 @@ def main():
 
     import bench as headline
     from gt4py_b200 import runtime, storage
-    from gt4py_b200.distributed import HaloExchanger, SlabDecomposition
+    from gt4py_b200.distributed import HaloExchanger, PeerHalo, SlabDecomposition
     from gt4py_b200.stencil import B200Stencil
 
     rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -206,15 +207,24 @@ def main():
             if p["t"] == "field":
                 buffers.setdefault(s["binding"][p["name"]], p["dtype"])
     opts = {"device_sync": False, **json.loads(args.options)}
+    # --peer (N > 1): exchanged fields in symmetric memory, halo rows pushed by the neighbours (b200_halo_push) and consumed
+    # inside the stencil launch (halo_wait kernels) or behind a one-thread wait kernel — no NCCL call on the data path
+    peer, exchanged = None, {f for fl in w["exchanges"].values() for f, _h in fl}
+    if args.peer and world > 1 and w["exchanges"]:
+        peer = PeerHalo(SlabDecomposition(world, rank, nj * world), nj)
     # two rotating buffer sets (working set >> L2)
     rng = np.random.default_rng(rank)
     sets = []
     for _ in range(2):
         host = make_inputs(buffers, shape, rng)
-        sets.append({n: storage.from_array(a, aligned_index=origin3) for n, a in host.items()})
+        sets.append({n: (peer.from_array(a, aligned_index=origin3) if (peer is not None and n in exchanged) else storage.from_array(a, aligned_index=origin3))
+                     for n, a in sorted(host.items())})  # (sorted: symmetric allocations are collective, same order on every rank)
     frozen = []
-    for s in steps:
-        st = B200Stencil(s["ir"], opts, name=f"{s['fixture']}.{s['variant']}")
+    for k, s in enumerate(steps):
+        sopts = dict(opts)
+        if peer is not None and k in w["exchanges"]:
+            sopts["halo_wait"] = True
+        st = B200Stencil(s["ir"], sopts, name=f"{s['fixture']}.{s['variant']}")
         frozen.append((st.freeze(origin={p: origin3 for p in s["binding"]}, domain=(ni, nj, nk)), default_params(s["ir"], s["fixture"]), st))
     exchanger = None
     lib = runtime.load_library()
@@ -222,7 +232,8 @@ def main():
     if world > 1 and w["exchanges"]:
         import ctypes
 
-        exchanger = HaloExchanger(SlabDecomposition(world, rank, nj * world), nj)
+        if peer is None:
+            exchanger = HaloExchanger(SlabDecomposition(world, rank, nj * world), nj)
         ev = [ctypes.c_void_p(), ctypes.c_void_p()]
         for e in ev:
             runtime.check(lib.b200_event_create(ctypes.byref(e)))
@@ -231,6 +242,17 @@ def main():
         bufs = sets[i & 1]
         n = 0
         for k, (s, (fr, params, _)) in enumerate(zip(steps, frozen)):
+            if exchange and peer is not None and k in w["exchanges"]:
+                runtime.check(lib.b200_event_record(ev[0], main_stream))
+                runtime.check(lib.b200_stream_wait_event(peer.stream, ev[0]))
+                n += peer.push([(bufs[f], hj, h) for f, h in w["exchanges"][k]])
+                st = frozen[k][2]
+                if all(kk["kind"] == "stream" for kk in st.compiled.plan["kernels"]):  # every kernel waits for itself
+                    n += fr(**{p: bufs[b] for p, b in s["binding"].items()}, **params, halo_wait=peer.wait_args())
+                else:
+                    n += peer.wait(main_stream)
+                    n += fr(**{p: bufs[b] for p, b in s["binding"].items()}, **params)
+                continue
             if exchange and exchanger is not None and k in w["exchanges"]:
                 runtime.check(lib.b200_event_record(ev[0], main_stream))
                 runtime.check(lib.b200_stream_wait_event(exchanger.stream, ev[0]))
@@ -294,6 +316,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": w["label"], "domain_per_gpu": [ni, nj, nk], "halo": list(w["halo"]),
                        "stencils": [s["fixture"] for s in steps], "codegen_options": opts,
+                       "exchange": None if world == 1 or not w["exchanges"] else ("peer-memory pushes (b200_halo_push, symmetric memory) consumed by halo_wait kernels" if peer is not None else "NCCL SendRecv (b200_halo_exchange), serial"),
                        "kernels": [st.compiled.kernel_names() for _, _, st in frozen],
                        "l2": "two rotating buffer sets, each larger than the 126 MB L2"},
             "gpu_launches": launches,
@@ -307,6 +330,8 @@ def main():
         print(json.dumps(line))
     if exchanger is not None:
         exchanger.close()
+    if peer is not None:
+        peer.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

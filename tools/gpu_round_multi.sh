@@ -1,10 +1,8 @@
 #!/usr/bin/env bash
 # Multi-GPU part of a round's device session (charged N x box time: keep it short).  From the repo root:
-#
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_round_multi.sh r02 2 2>&1 | tail -40'
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tools/gpu_round_multi.sh r02 8 2>&1 | tail -40'
 set -u
-TAG="${1:-rXX}"; N="${2:-2}"
+TAG="${1:-rXX}"; N="${2:-2}"; WHAT="${3:-all}"
 OUT=gpurun_out; mkdir -p "$OUT"
 PORT=29541
 run() {  # run <seconds> <name> <script and args...>
@@ -13,17 +11,16 @@ run() {  # run <seconds> <name> <script and args...>
   timeout "$t" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port "$PORT" "$@" \
       > "$OUT/${TAG}_n${N}_${name}.log" 2>&1
   echo "    exit $? after $((SECONDS - t0))s"; PORT=$((PORT + 1))
-  grep -h '"metric"' "$OUT/${TAG}_n${N}_${name}.log" | cut -c1-700
+  grep -h '"metric"' "$OUT/${TAG}_n${N}_${name}.log" | python -c "
+import json, sys
+for l in sys.stdin:
+    d = json.loads(l); c = d['config']
+    print(json.dumps({'value': d['value'], 'ms_per_step': d['ms_per_step'], 'kernel_ms': d['roofline']['kernel_ms'], 'parallelism': c['parallelism'][:90],
+                      'trial': c.get('schedule_trial'), 'check': c.get('multi_gpu_check'), 'exposed_us': c.get('exposed_comm_us_per_step'), 'note': d['e2e'].get('note')}))
+" 2>/dev/null || tail -5 "$OUT/${TAG}_n${N}_${name}.log" | cut -c1-400
 }
-python - <<'PY'
-import __graft_entry__ as g
-g.build()
-PY
-run 300 bench        bench.py --gpus "$N" --steps 50 --warmup 5              # schedule trial: serial / overlap / thin
+run 300 bench        bench.py --gpus "$N" --steps 50 --warmup 5              # schedule trial: serial / overlap / thin / peer
+if [ "$WHAT" = "all" ]; then
+run 200 bench_peer   bench.py --gpus "$N" --steps 50 --warmup 5 --step-mode peer --no-autotune
 run 200 bench_serial bench.py --gpus "$N" --steps 50 --warmup 5 --step-mode serial --no-autotune
-run 200 bench_thin   bench.py --gpus "$N" --steps 50 --warmup 5 --step-mode thin --no-autotune
-run 200 exchange     tools/bench_exchange.py
-run 200 x2           tools/bench_workloads.py --workload hdiff_x2 --steps 20          # two 2-row exchanges per pass
-run 200 x2_fused     tools/bench_workloads.py --workload hdiff_x2 --fuse --steps 20   # one 4-row exchange per pass
-run 200 cfg4         tools/bench_workloads.py --workload upwind5 --steps 20
-run 200 cfg5         tools/bench_workloads.py --workload fastwaves --steps 10
+fi
