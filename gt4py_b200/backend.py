@@ -288,6 +288,7 @@ class B200Backend(BaseBackend):
         "tma_rows": {"versioning": True, "type": int},
         "tma_mode": {"versioning": True, "type": str},  # "tensor" (cp.async.bulk.tensor) | "bulk" (one cp.async.bulk per row)
         "tma_smem_kb": {"versioning": True, "type": int},
+        "uniform_task": {"versioning": True, "type": bool},  # task index from a lane-0 shuffle: uniform-datapath addressing
         "halo_wait": {"versioning": True, "type": bool},  # multi-GPU: boundary tiles wait for the neighbours' pushed halo rows
         "row_pointers": {"versioning": True, "type": bool},
         "fuse_columns": {"versioning": True, "type": bool},
@@ -307,7 +308,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "extra_opt_flags", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait", "uniform_task")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -322,7 +322,7 @@ class StreamKernel:
         for v in self.values:
             req[id(v)] = v.window + (pf if v.kind == "in" else 0)
         best = None
-        for P in (1, 2, 3, 4, 6):
+        for P in (1, 2, 3, 4, 6, 8):  # (8: a 7-row window + 1 prefetch row rotates instead of shifting: upwind5's phi)
             divs = [d for d in range(1, P + 1) if P % d == 0]
             cost, assign = 0, {}
             for v in self.values:
@@ -395,7 +395,15 @@ class StreamKernel:
             w("  const int QX0 = QXF;")
         w("  const int nseg = ((X1 - QX0 * V) + SQ * V - 1) / (SQ * V);")
         w("  const int ntj = (Y1 - Y0 + TJ - 1) / TJ;")
-        w("  const long long task = (long long)blockIdx.x * NW + threadIdx.y;")
+        if self.opts.get("tma") or self.opts.get("uniform_task", True):
+            # warp-uniform by construction (a shuffle from lane 0): everything derived from it — task, segment, tile, level,
+            # march step, row base addresses, ring slot — stays in uniform registers: hdiff 64 -> 44 registers (32 -> 44 resident
+            # warps per SM) and 0.85 -> 0.91 of the HBM peak (profiles/README.md r02k); the bulk-copy operands of the `tma`
+            # variant need no per-lane waterfall loop.  `uniform_task=False` keeps the plain threadIdx.y form.
+            w("  const int wy = __shfl_sync(0xffffffffu, (int)threadIdx.y, 0);")
+        else:
+            w("  const int wy = threadIdx.y;")
+        w("  const long long task = (long long)blockIdx.x * NW + wy;")
         w(f"  const int nk = {A}.g.k_hi - {A}.g.k_lo;")
         w("  if (task >= (long long)nseg * ntj * nk) return;")
         halo_wait = bool(self.opts.get("halo_wait", False))
@@ -417,7 +425,8 @@ class StreamKernel:
         k0 = cg._bound(self.interval[0], f"{A}.g.nK")
         k1 = cg._bound(self.interval[1], f"{A}.g.nK")
         w(f"  if (k < {k0} || k >= {k1}) return;")
-        w("  const int g0 = (QX0 + seg * SQ - HL + lane) * V;   // first I index of this lane's vector")
+        w("  const int g0w = (QX0 + seg * SQ - HL) * V;   // first I index of the warp's row segment (warp-uniform)")
+        w("  const int g0 = g0w + lane * V;   // first I index of this lane's vector")
         w("  const bool own = (lane >= HL) && (lane < HL + SQ);")
         w("  const int T_lo = Y0 + tj * TJ;")
         w("  const int T_hi = (T_lo + TJ < Y1) ? T_lo + TJ : Y1;")
@@ -560,12 +569,12 @@ class StreamKernel:
                     # packed back to back in the slot (coordinates are array indices: domain index + origin)
                     for n, v in enumerate(ins):
                         m = gen.tmap_index(v.field, 32 * V, UT)
-                        w(f"{pad}b200::tma_load_3d({slot_expr} + {n * UT * RB}, &A.tm[{m}], g0 + A.tmo[{m}][0], "
+                        w(f"{pad}b200::tma_load_3d({slot_expr} + {n * UT * RB}, &A.tm[{m}], g0w + A.tmo[{m}][0], "
                           f"({first_step} - ({v.lag})) + A.tmo[{m}][1], (k + ({v.dk}) + A.tmo[{m}][2]) * A.tmo[{m}][3], {bar});")
                     return
                 for n, v in enumerate(ins):
                     pitch = "SJ" if self.SJ else f"sj_{v.cname}"
-                    w(f"{pad}{{ const {CT[v.dtype]}* src = p_{v.cname} + (long long)({first_step} - ({v.lag})) * {pitch} + g0;")
+                    w(f"{pad}{{ const {CT[v.dtype]}* src = p_{v.cname} + (long long)({first_step} - ({v.lag})) * {pitch} + g0w;")
                     for u in range(UT):
                         w(f"{pad}  b200::bulk_g2s({slot_expr} + {(n * UT + u) * RB}, src + {u} * {pitch}, {RB}, {bar});")
                     w(f"{pad}}}")
@@ -573,15 +582,17 @@ class StreamKernel:
             w(f"  if ({cond}) {{   // steady loop (interior, bulk-async ring: {D} slots of {UT} rows x {NS} streams per warp)")
             w(f"    const int t_tma_end = (t_int > t) ? t + ((t_int - t) / {UT}) * {UT} : t;   // first step after the steady trips")
             w("    if (t_tma_end > t) {")
-            w(f"      unsigned char* rp = &b200_ring[threadIdx.y][0] + lane * {RB // 32};   // this lane's vector in the current slot")
+            w(f"      unsigned char* rpw = &b200_ring[wy][0];   // the current slot of this warp's ring (warp-uniform)")
+            w(f"      unsigned char* rp = rpw + lane * {RB // 32};   // this lane's vector in it")
             w("      int sl = 0;")
             w("      unsigned par = 0u;")
-            w("      if (lane == 0) {")
-            w(f"        for (int d = 0; d < {D}; ++d) b200::mbar_init(&b200_bar[threadIdx.y][d], 1);")
+            w("      const bool issuer = b200::elect_one();   // one lane issues the copies")
+            w("      if (issuer) {")
+            w(f"        for (int d = 0; d < {D}; ++d) b200::mbar_init(&b200_bar[wy][d], 1);")
             w("        b200::mbar_fence_init();")
             for d in range(D):
                 w(f"        if (t + {d * UT} < t_tma_end) {{")
-                issue(f"rp + {d * slot_bytes}", f"&b200_bar[threadIdx.y][{d}]", f"t + {d * UT}", "          ")
+                issue(f"rpw + {d * slot_bytes}", f"&b200_bar[wy][{d}]", f"t + {d * UT}", "          ")
                 w("        }")
             w("      }")
             w("      __syncwarp();")
@@ -590,23 +601,23 @@ class StreamKernel:
             w("        B200_TRACE(5);")
             if not self._useq:
                 w("        const long long toff = (long long)t * SJ + g0;   // this trip's row offset, shared by all streams")
-            w("        b200::mbar_wait(&b200_bar[threadIdx.y][sl], par);   // the rows of this trip have landed")
+            w("        b200::mbar_wait(&b200_bar[wy][sl], par);   // the rows of this trip have landed")
             for u in range(UT):
                 w(f"        {{  // steady step, rotation phase {(ph0 + u) % U}")
                 w(f"          const int tt = t + {u};")
                 L.extend(self._emit_step((ph0 + u) % U, fast="interior", u=u))
                 w("        }")
             w("        __syncwarp();   // every lane has read the slot: it may be refilled")
-            w(f"        if (lane == 0 && t + {D * UT} < t_tma_end) {{")
+            w(f"        if (issuer && t + {D * UT} < t_tma_end) {{")
             if self.opts.get("tma_fence", True):
                 w("          b200::fence_async_smem();")
-            issue("rp", "&b200_bar[threadIdx.y][sl]", f"t + {D * UT}", "          ")
+            issue("rpw", "&b200_bar[wy][sl]", f"t + {D * UT}", "          ")
             w("        }")
             if self.SJ and self._useq:
                 for v in streams:
                     w(f"        q_{v.cname} += {UT} * SJ;")
-            w(f"        ++sl; rp += {slot_bytes};")
-            w(f"        if (sl == {D}) {{ sl = 0; rp -= {D * slot_bytes}; par ^= 1u; }}")
+            w(f"        ++sl; rp += {slot_bytes}; rpw += {slot_bytes};")
+            w(f"        if (sl == {D}) {{ sl = 0; rp -= {D * slot_bytes}; rpw -= {D * slot_bytes}; par ^= 1u; }}")
             w("      }")
             w("    }")
             w("  }")

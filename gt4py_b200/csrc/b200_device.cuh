@@ -108,6 +108,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const TMap* tm, int c0, i
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// true in exactly one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
   unsigned ok;
   asm volatile(
@@ -124,6 +130,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #else
 // CPU emulation (tests/emu): copies complete at issue; a barrier word counts completed phases (low half) and
 // pending transaction bytes (high half), so a wait on the wrong parity / an overrun producer aborts the test.
+__device__ __forceinline__ bool elect_one() { return emu::lane() == 0; }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
 __device__ __forceinline__ void mbar_fence_init() {}
 __device__ __forceinline__ void fence_async_smem() {}

@@ -358,21 +358,23 @@ class B200Stencil:
         {"interior_loop": True, "static_pitch": "auto", "min_blocks": 8, "tile_j": 128},
         {"interior_loop": True, "static_pitch": "auto", "min_blocks": 9},
         {"interior_loop": True, "static_pitch": "auto", "tile_j": 256},
-        # bulk-async variants (codegen_stream.py: tensor-map copies into a per-warp shared-memory ring, LDS reads)
+        # bulk-async variants (codegen_stream.py: bulk / tensor-map copies into a per-warp shared-memory ring, LDS reads)
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk"},
         {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "tile_j": 32, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 48, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 24, "prefetch": 1},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk"},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 48, "prefetch": 1, "tma_mode": "bulk"},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 24, "prefetch": 1, "tma_mode": "bulk"},
         {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 16, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "tile_j": 48, "prefetch": 1},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "warps": 2},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 4, "prefetch": 1, "tma_mode": "bulk"},
         {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "l2_prefetch": 4},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "stcs": True},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "tma_rows": 8, "tma_smem_kb": 48},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3},
-        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "warps": 2},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk", "stcs": True},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 0},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 0, "tma_mode": "bulk"},
+        {"interior_loop": True, "static_pitch": "auto", "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk", "tma_rows": 8, "tma_smem_kb": 48},
+        {"interior_loop": True, "static_pitch": "auto", "uniform_task": False},  # (the round-1 addressing, for the record)
+        {"interior_loop": True, "static_pitch": "auto", "min_blocks": 10},
+        {"interior_loop": True, "static_pitch": "auto", "min_blocks": 12},
+        {"interior_loop": True, "static_pitch": "auto", "prefetch": 2},
         {"edge_loop": True},
         {"pure_loop": False},
         {"vector_width": 4},

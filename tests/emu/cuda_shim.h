@@ -62,6 +62,7 @@ template <class T> inline T shfl(T v, int src) {
 }  // namespace emu
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l - d >= 0 ? l - d : l); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { int l = emu::lane(); return emu::shfl(v, l + d < 32 ? l + d : l); }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl(v, src); }
 inline bool __any_sync(unsigned, bool p) { return emu::any(p); }
 inline void __syncwarp(unsigned = 0xffffffffu) { (void)emu::any(false); }
 inline bool __all_sync(unsigned, bool p) { return !emu::any(!p); }

@@ -115,6 +115,43 @@ def test_hdiff_full_size_properties():
     assert torch.equal(out.torch()[h:-h, h:-h, :], const.torch()[h:-h, h:-h, :])
 
 
+def test_hdiff_full_size_whole_domain_against_the_oracle():
+    """BASELINE.json configs[1] at FULL size, every cell: the oracle (NumPy restatement of the reference numpy backend,
+    ~10 s for 84 M cells) against the variants that are actually timed — the backend's default (lazy per-pitch
+    specialisation: interior loop + compile-time pitch + uniform task index), the bulk-async (TMA) variants bench.py's
+    autotune selects among, and the `halo_wait` kernel of the multi-GPU schedule — all bit for bit."""
+    import torch
+
+    from gt4py_b200.stencil import B200Stencil
+    from oracle import numpy_oracle
+
+    st = testing.load_ir("hdiff_f32", "staged")
+    n, nk, h = 1024, 80, 2
+    if __import__("os").environ.get("B200_EMULATE_DEVICE") == "1":  # logic check of this test on the fake device
+        n, nk = 130, 3
+    rng = np.random.default_rng(17)
+    shape = (n + 2 * h, n + 2 * h, nk)
+    origin = {k: (h, h, 0) for k in ("in_field", "out_field", "coeff")}
+    host = {"in_field": rng.random(shape, dtype=np.float32), "coeff": rng.random(shape, dtype=np.float32) * np.float32(0.1),
+            "out_field": np.zeros(shape, np.float32)}  # fmt: skip
+    inp = storage.from_array(host["in_field"], aligned_index=(h, h, 0))
+    coeff = storage.from_array(host["coeff"], aligned_index=(h, h, 0))
+    numpy_oracle.run(st, host, {}, (n, n, nk), origin)
+    want = torch.from_numpy(host["out_field"]).to(inp._base.device)
+    pitch = inp.element_strides[1]
+    P = {"interior_loop": True, "static_pitch": pitch}
+    variants = [{"specialize": "lazy"}, dict(P), {**P, "tma": 3, "tile_j": 32, "prefetch": 1}, {**P, "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk"},
+                {**P, "tma": 4, "prefetch": 1}, {**P, "halo_wait": True}, {**P, "uniform_task": False}]  # fmt: skip
+    for opts in variants:
+        out = storage.zeros(shape, np.float32, aligned_index=(h, h, 0))
+        stencil = B200Stencil(st, {"strategy": "auto", **opts})
+        stencil(inp, out, coeff, origin=origin, domain=(n, n, nk))
+        got = out.torch()
+        assert torch.equal(got, want), f"{opts}: {(got != want).sum().item()} cells differ from the oracle"
+        if opts.get("specialize") == "lazy":  # the default really ran the specialised kernels
+            assert stencil.compiled._special and next(iter(stencil.compiled._special.values())).options.get("static_pitch") == pitch
+
+
 @pytest.mark.parametrize("name,variant", [("hdiff_f32", "staged"), ("hdiff_f32", "default"), ("fw_pgrad_f32", "staged"), ("upwind5_f32", "staged")])
 def test_subbox_launches_compose_to_the_full_domain(name, variant):
     """`b200_stencil_run(..., subbox)` (used to overlap the halo exchange with interior compute):

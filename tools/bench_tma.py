@@ -20,19 +20,17 @@ WORKLOADS = {
     "div": ("fw_div_f32", "staged", (4096, 512, 80)),
 }
 P = {"interior_loop": True, "static_pitch": "auto"}
-T2, T3 = {**P, "tma": 2}, {**P, "tma": 3}  # tensor-map copies (one per stream and trip); "tma_mode": "bulk" = one 1-D copy per row
+U = dict(P)  # (uniform_task is the default now; {"uniform_task": False} = the round-1 addressing)
+T3 = {**P, "tma": 3, "tile_j": 32, "prefetch": 1}  # tensor-map copies (one per stream and trip) into a ring of 3 trips
 CANDIDATES = [
     {}, dict(P), {**P, "min_blocks": 8}, {"interior_loop": "steady", "static_pitch": "auto", "row_pointers": True},
-    {**T3, "prefetch": 1, "tma_mode": "bulk"}, {**T2, "tma_mode": "bulk"},
-    dict(T2), dict(T3), {**P, "tma": 4}, {**T2, "prefetch": 1}, {**T3, "prefetch": 1}, {**P, "tma": 4, "prefetch": 1},
-    {**T3, "tma_rows": 12}, {**T2, "tma_rows": 12}, {**T3, "prefetch": 1, "tma_rows": 8, "tma_smem_kb": 48}, {**T3, "tma_rows": 3}, {**P, "tma": 4, "tma_rows": 3},
-    {**T3, "min_blocks": 8}, {**T3, "prefetch": 1, "min_blocks": 8}, {**T3, "row_pointers": True}, {**T3, "row_pointers": True, "prefetch": 1},
-    {"interior_loop": "steady", "static_pitch": "auto", "row_pointers": True, "tma": 3},
-    {"interior_loop": "steady", "static_pitch": "auto", "row_pointers": True, "tma": 3, "prefetch": 1},
-    {**T3, "tile_j": 32}, {**T3, "tile_j": 128}, {**T3, "tile_j": 32, "prefetch": 1}, {**T3, "tile_j": 128, "prefetch": 1},
-    {**T3, "warps": 2}, {**T3, "warps": 8, "tma_smem_kb": 48}, {**T3, "warps": 2, "prefetch": 1}, {**T3, "warps": 1}, {**T3, "warps": 1, "prefetch": 1},
-    {**T2, "vector_width": 4, "warps": 2}, {**T3, "vector_width": 4, "tma_rows": 3}, {**T3, "vector_width": 4, "warps": 2, "prefetch": 1},
-    {**T3, "stcs": True}, {**T3, "tma_fence": False},
+    {"uniform_task": False}, {**P, "uniform_task": False}, {**U, "min_blocks": 9}, {**U, "min_blocks": 10}, {**U, "min_blocks": 12}, {**U, "l2_prefetch": 4}, {**U, "l2_prefetch": 1},
+    {**U, "prefetch": 2}, {**U, "prefetch": 0}, {**U, "prefetch": 2, "l2_prefetch": 4}, {**U, "vector_width": 4}, {**U, "vector_width": 4, "prefetch": 0},
+    {**T3, "tma_mode": "bulk", "tma": 4}, {**T3, "tma_mode": "bulk", "tile_j": 16}, {**T3, "tma_mode": "bulk", "tile_j": 24}, {**T3, "tma_mode": "bulk", "tile_j": 48}, {**T3, "tma_mode": "bulk", "prefetch": 0}, {**U, "row_pointers": True},
+    {**U, "tile_j": 32}, {**U, "tile_j": 128}, {**U, "warps": 2}, {**U, "warps": 8}, {**U, "stcs": True}, {**U, "warps": 8, "l2_prefetch": 4},
+    dict(T3), {**T3, "tma": 4}, {**T3, "tile_j": 48}, {**T3, "tile_j": 24}, {**T3, "tile_j": 16}, {**T3, "tile_j": 64, "tma": 4}, {**T3, "tile_j": 64, "tma": 5, "warps": 2},
+    {**T3, "warps": 2}, {**T3, "warps": 8, "tma_smem_kb": 48}, {**T3, "prefetch": 0}, {**T3, "prefetch": 0, "tma": 4}, {**T3, "tma_rows": 8, "tma_smem_kb": 48},
+    {**T3, "tma_fence": False}, {**T3, "min_blocks": 9}, {**T3, "stcs": True}, {**T3, "l2_prefetch": 4}, {**T3, "tma": 3, "tma_mode": "bulk"},
 ]
 
 
