@@ -120,8 +120,10 @@ def recompute_extents(stencil: Dict[str, Any]) -> Dict[str, Extent]:
     block extent + offset.  Sets he["extent"] and the temporaries' "extent"; returns field -> extent
     (for API fields: the halo the caller must provide)."""
     need: Dict[str, Extent] = {}
-    hes = [he for *_x, he in b2ir.iter_hes(stencil)]
-    for he in reversed(hes):
+    # the reference's traversal (StencilExtentComputer, oir_optimizations/utils.py:276-300): vertical loops in reverse,
+    # the sections of a loop in FORWARD order (no visitor reverses them), the horizontal executions of a section in reverse
+    hes = [he for loop in reversed(stencil["loops"]) for sec in loop["sections"] for he in reversed(sec["hes"])]
+    for he in hes:
         acc = b2ir.field_accesses(he["body"])
         ext = _zero()
         for a in acc:
