@@ -289,6 +289,11 @@ class B200Backend(BaseBackend):
         "tma_mode": {"versioning": True, "type": str},  # "tensor" (cp.async.bulk.tensor) | "bulk" (one cp.async.bulk per row)
         "tma_smem_kb": {"versioning": True, "type": int},
         "uniform_task": {"versioning": True, "type": bool},  # task index from a lane-0 shuffle: uniform-datapath addressing
+        "div_inv": {"versioning": True, "type": bool},  # divisions by launch-invariant divisors through the hoisted reciprocal (default on)
+        "div_slow": {"versioning": True, "type": str},  # "call" | "inline": where the IEEE fallback of those divisions lives
+        "period": {"versioning": True, "type": int},  # streaming kernels: force the unroll factor of the march loop
+        "k_order": {"versioning": True, "type": object},  # "auto" | bool: level-fastest task order (kernels reading at K offsets)
+        "col_smem": {"versioning": True, "type": object},  # "auto" | bool: temporaries of fused sweeps in shared memory
         "halo_wait": {"versioning": True, "type": bool},  # multi-GPU: boundary tiles wait for the neighbours' pushed halo rows
         "row_pointers": {"versioning": True, "type": bool},
         "fuse_columns": {"versioning": True, "type": bool},
@@ -308,7 +313,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "extra_opt_flags", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait", "uniform_task")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait", "uniform_task", "div_inv", "div_slow", "period", "k_order", "col_smem")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -109,6 +109,27 @@ class ExprGen:
         self.written = written  # fields written by the current kernel (no read-only loads)
         self.i, self.j, self.k, self.A = ivar, jvar, kvar, args
         self.locals: Dict[str, str] = {}
+        #: callable(C expression of a launch-invariant divisor) -> name of its hoisted b200::DivInv, or None: plain division
+        self.div_hoist = None
+        #: callable(C expression of the dividend, DivInv name, C type) -> name of the quotient variable, or None: b200::div_inv
+        self.div_group = None
+
+    def invariant(self, n) -> bool:
+        """The expression has the same value for every cell of a launch: literals and scalar parameters only."""
+        t = n["t"]
+        if t == "lit":
+            return True
+        if t == "scalar":
+            return n["name"] not in self.locals
+        if t in ("cast", "unary"):
+            return self.invariant(n["expr"])
+        if t == "binary":
+            return self.invariant(n["left"]) and self.invariant(n["right"])
+        if t == "ternary":
+            return self.invariant(n["cond"]) and self.invariant(n["true"]) and self.invariant(n["false"])
+        if t == "call":
+            return all(self.invariant(a) for a in n["args"])
+        return False
 
     # -- addressing ---------------------------------------------------------------------------
     def field_ref(self, node, *, for_write=False) -> str:
@@ -188,6 +209,13 @@ class ExprGen:
             if op == "/" and dt.startswith("int"):
                 # NumPy true-divide then store into an integer: truncation toward zero == C division
                 return f"((({b}) == 0) ? ({CT[dt]})0 : ({CT[dt]})(({a}) / ({b})))"
+            if op == "/" and dt in ("float32", "float64") and self.div_hoist is not None and self.invariant(n["right"]):
+                # the divisor is the same for every cell of the launch: hoisted with its reciprocal, 3 FP
+                # instructions per cell, bit-equal to the IEEE division (b200_device.cuh, DivInv)
+                dv = self.div_hoist(f"({CT[dt]})({b})")
+                if self.div_group is not None:  # the emitter guards a whole group of quotients with one branch
+                    return self.div_group(f"({CT[dt]})({a})", dv, CT[dt])
+                return f"b200::div_inv(({CT[dt]})({a}), {dv})"
             return f"(({a}) {op} ({b}))"
         if t == "ternary":
             ct = CT[n["dtype"]]

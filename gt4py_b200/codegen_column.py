@@ -82,6 +82,7 @@ class ColumnKernel:
         # fields also read straight from memory (variable / absolute K index): their stores are
         # never deferred, so those reads always see the latest value
         self.direct_read: Set[str] = {a["name"] for a in acc if not a["write"] and isinstance(a["off"], dict)}
+        self.div_hoisted: Dict[str, str] = {}
         pf = opts.get("seq_prefetch", True)
         self.depth = max(0, int(pf)) if not isinstance(pf, bool) else (1 if pf else 0)  # levels of load look-ahead
         self.prefetch = self.depth > 0
@@ -133,6 +134,8 @@ class ColumnKernel:
                 super().__init__(kern.ft, kern.written, args="A")
                 self.pre: List[str] = []
                 self.ind = "      "
+                if kern.opts.get("div_inv", True):  # divisors that are launch invariants: hoisted reciprocal (b200::DivInv)
+                    self.div_hoist = lambda cx: kern.div_hoisted.setdefault(cx, f"dv{len(kern.div_hoisted)}")
 
             def field_load(self, node):
                 off = node["off"]
@@ -270,6 +273,7 @@ class ColumnKernel:
         w(f"  const int i = A.g.i_lo + ({ei0}) + (int)(blockIdx.x * {bx} + threadIdx.x);")
         w(f"  const int j = A.g.j_lo + ({ej0}) + (int)(blockIdx.y * {by} + threadIdx.y);")
         w(f"  if (i >= A.g.i_hi + ({ei1}) || j >= A.g.j_hi + ({ej1})) return;")
+        div_marker = len(L)
         for fname in sorted(self.cacheable):
             n = self.ft.index[fname]
             ct = CT[self.ft.entries[n]["dtype"]]
@@ -321,6 +325,7 @@ class ColumnKernel:
             w("    }")
             w("  }")
         w("}")
+        L[div_marker:div_marker] = [f"  const auto {nm} = b200::div_inv_make({cx});" for cx, nm in self.div_hoisted.items()]
         gen.src.append("\n".join(L))
         gen.live |= {a["name"] for he in self.hes for a in b2ir.field_accesses(he["body"])}
         gen.kernels.append(

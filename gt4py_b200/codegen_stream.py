@@ -304,6 +304,11 @@ class StreamKernel:
             self.SQ -= 1
         self._choose_windows()
         self.TJ = int(self.opts.get("tile_j", 64))
+        # a section of one or two levels (the top / bottom level of a K-dependent computation) has few tasks: shorter J
+        # tiles, or its launch is a fraction of a wave of warps that each march 64 rows (75 us for one 4096 x 512 plane)
+        (b0, o0), (b1, o1) = self.interval
+        if b0 == b1 and 0 < o1 - o0 <= 2 and "tile_j" not in self.opts:
+            self.TJ = 8
         self.NW = int(self.opts.get("warps", 4))
 
     def _pf(self) -> int:
@@ -322,7 +327,25 @@ class StreamKernel:
         for v in self.values:
             req[id(v)] = v.window + (pf if v.kind == "in" else 0)
         best = None
+        # the march loop is unrolled P times: its code must stay well inside the 32 KB instruction cache of an SM (L1.5),
+        # warps of a CTA sit at different places of the loop.  Measured (profiles/README.md r02m): upwind5 with P = 8 is a
+        # 30 KB loop — 49 % instruction-cache hit rate, "no instruction" the top stall, 2.8 ms; P = 4 with phi's window
+        # shifting: 1.7 ms.  Rough size of one step: 16 bytes x V x (operations + shuffles/loads/stores).
+        ops = [0]
+
+        def count(n):
+            if n["t"] in ("binary", "unary", "ternary", "call", "cast"):
+                ops[0] += 6 if (n["t"] == "binary" and n["op"] == "/") else (12 if n["t"] == "call" else 1)
+            elif n["t"] == "field":
+                ops[0] += 1
+
+        for he in self.hes:
+            b2ir.walk_exprs(he["body"], count)
+        step_bytes = 16 * (self.V * ops[0] + 8 * len([v for v in self.values if v.kind == "in" or v.store]))
+        forced = int(self.opts.get("period", 0) or 0)  # option `period`: force the unroll factor (device sweeps)
         for P in (1, 2, 3, 4, 6, 8):  # (8: a 7-row window + 1 prefetch row rotates instead of shifting: upwind5's phi)
+            if forced and P != forced:
+                continue
             divs = [d for d in range(1, P + 1) if P % d == 0]
             cost, assign = 0, {}
             for v in self.values:
@@ -335,6 +358,7 @@ class StreamKernel:
                     assign[id(v)] = (r, True)
                     cost += 3 * r
             cost += 0.25 * P  # code size
+            cost += max(0.0, (P * step_bytes - 14 * 1024) / 1024.0) * 2.0  # instruction-cache pressure beyond ~14 KB of loop
             if best is None or cost < best[0]:
                 best = (cost, P, assign)
         _, self.U, assign = best
@@ -379,6 +403,11 @@ class StreamKernel:
         w(f'extern "C" __global__ void {lb} {name}(const __grid_constant__ Args A) {{')
         w(f"  constexpr int V = {V}, SQ = {self.SQ}, HL = {self.hl}, TJ = {self.TJ}, NW = {self.NW};")
         w("  const int lane = threadIdx.x;")
+        # divisions by launch-invariant divisors (scalar parameters / literals: grid spacings, time steps): the divisor and
+        # its correctly rounded reciprocal are set up once per thread HERE (the lines are inserted when the march steps
+        # have been emitted), every cell then pays 3 FP instructions instead of an IEEE division sequence (b200::DivInv)
+        self.div_hoisted: Dict[str, str] = {}
+        div_marker = len(L)
         # owned output box of this launch: union of the storing stages' extents
         st_stages = sorted({v.stage for v in self.values if v.store})
         ei0 = min(self.hes[s]["extent"][0][0] for s in st_stages)
@@ -407,7 +436,27 @@ class StreamKernel:
         w(f"  const int nk = {A}.g.k_hi - {A}.g.k_lo;")
         w("  if (task >= (long long)nseg * ntj * nk) return;")
         halo_wait = bool(self.opts.get("halo_wait", False))
-        if halo_wait:
+        # task order.  Default: segment fastest, level slowest (plane by plane).  A kernel that reads a field at K offsets
+        # (pp[0,0,+-1] of the pressure gradient) touches every plane of that field from three levels: with the LEVEL
+        # fastest, the warps of a CTA and of its neighbours work on consecutive levels of the same rows at the same time,
+        # so the second and third read of a row hit L1 / L2 instead of HBM (plane by plane the re-use distance is two
+        # whole planes of every streamed field: 37 instead of 28 B/cell of DRAM traffic, profiles/README.md r02m)
+        kfast = self.opts.get("k_order", "auto")
+        kfast = any(v.kind == "in" and v.dk != 0 for v in self.values) if kfast == "auto" else bool(kfast)
+        self.kfast = kfast
+        if halo_wait and kfast:
+            w("  int seg, tj, kk;")
+            w("  if (ntj >= 3) {")
+            w("    const long long n_int = (long long)nseg * (ntj - 2) * nk;   // interior tiles first")
+            w("    if (task < n_int) { kk = (int)(task % nk); const long long r = task / nk; seg = (int)(r % nseg); tj = 1 + (int)(r / nseg); }")
+            w("    else { const long long tb = task - n_int; kk = (int)(tb % nk); const long long r = tb / nk; seg = (int)(r % nseg); tj = ((r / nseg) & 1) ? ntj - 1 : 0; }")
+            w("  } else { kk = (int)(task % nk); const long long r = task / nk; seg = (int)(r % nseg); tj = (int)(r / nseg); }")
+            w(f"  const int k = {A}.g.k_lo + kk;")
+        elif kfast:
+            w(f"  const int k = {A}.g.k_lo + (int)(task % nk);")
+            w("  const int seg = (int)((task / nk) % nseg);")
+            w("  const int tj = (int)(task / ((long long)nk * nseg));")
+        elif halo_wait:
             # multi-GPU J slabs with the peer-memory halo exchange: the first and the last J tile read rows the neighbours
             # push into this rank's halo while this kernel is already running -> those tiles come LAST in the task order
             # (all levels), behind every interior tile, so that by the time they start their halo has normally arrived
@@ -710,6 +759,7 @@ class StreamKernel:
         if interior and not steady_only:
             w("  }")
         w("}")
+        L[div_marker:div_marker] = [f"  const auto {nm} = b200::div_inv_make({cx});" for cx, nm in self.div_hoisted.items()]
         gen.src.append("\n".join(L))
         gen.live |= {v.field for v in self.values if v.kind == "in" or v.store} | self.direct
         gen.kernels.append(
@@ -856,6 +906,9 @@ class StreamKernel:
                 super().__init__(kern.ft, set(), args="A")
                 self.elem = elem
                 self.pre: List[str] = []
+                if kern.opts.get("div_inv", True):
+                    self.div_hoist = lambda cx: kern.div_hoisted.setdefault(cx, f"dv{len(kern.div_hoisted)}")
+                    self.div_group = self._div_group
                 self.k = "k"
                 self.i = f"(g0 + {elem})"
                 self.j = "r"
@@ -878,6 +931,15 @@ class StreamKernel:
                     self.pre.append(f"const {CT[v.dtype]} {nm} = {fn}(0xffffffffu, {kern.reg(v, slot, src)}, {abs(dl)});")
                 return nm
 
+            def _div_group(self, a: str, dv: str, ct: str) -> str:
+                # quotients by a launch-invariant divisor: computed ahead of the statement (like the shuffles); the
+                # statement's whole group — all V elements — shares one range check (flush_pre)
+                nm = f"dq{len(divq)}"
+                acc = f"dbad{divg[0]}{'f' if ct == 'float' else 'd'}"
+                divq.append((nm, dv, ct, acc))
+                self.pre.append(f"const {ct} {nm}_a = {a}; {ct} {nm} = b200::div_inv_try({nm}_a, {dv}, {acc});")
+                return nm
+
             def expr(self, n):
                 if n["t"] == "scalar" and n["name"] in self.locals:
                     return f"{self.locals[n['name']]}_{self.elem}"
@@ -890,11 +952,30 @@ class StreamKernel:
             ct = CT[d["dtype"]]
             L.append(ind2 + f"{ct} " + ", ".join(f"l_{d['name']}_{e} = ({ct})0" for e in range(V)) + ";")
 
+        divq: List[Tuple[str, str, str, str]] = []  # quotients of the stage so far: (name, DivInv, C type, accumulator)
+        divg = [0, 0]  # [current group index, first quotient of the current group]
+
         def flush_pre():
+            group = divq[divg[1]:]
+            for acc, ct in sorted({(q[3], q[2]) for q in group}):
+                L.append(ind2 + f"{'unsigned' if ct == 'float' else 'unsigned long long'} {acc} = 0;")
             for eg in egs:
                 for line in eg.pre:
                     L.append(ind2 + line)
                 eg.pre = []
+            if group:
+                # one (warp-uniform) branch for the group: some quotient left the guarded exponent range (zero, infinity,
+                # NaN, tiny, huge) -> the IEEE division for all of them, the same values where the fast path was valid
+                cond = " || ".join(f"b200::div_inv_bad({acc})" for acc in sorted({q[3] for q in group}))
+                L.append(ind2 + f"if (__builtin_expect(__any_sync(0xffffffffu, {cond}), 0)) {{")
+                for nm, dv, ct, acc in group:
+                    # (out-of-line: a call per quotient keeps the loop small but its ABI costs registers once the loop is
+                    #  unrolled 4+ times — 71 / 96 / 108 for upwind5 at period 2 / 4 / 8 — hence inline there)
+                    inline = kern.opts.get("div_slow", "call" if kern.U <= 2 else "inline") == "inline"
+                    L.append(ind2 + (f"  {nm} = {nm}_a / {dv}.d;" if inline else f"  {nm} = b200::div_ieee({nm}_a, {dv}.d);"))
+                L.append(ind2 + "}")
+                divg[0] += 1
+                divg[1] = len(divq)
 
         def emit_stmts(stmts, masks: List[Optional[str]]):
             # masks: per-element condition variable names (None = unconditional)

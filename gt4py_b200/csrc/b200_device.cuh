@@ -205,6 +205,69 @@ __device__ __forceinline__ int clampk(long long k, int lo, int hi) {
   return (int)(k < lo ? lo : (k > hi - 1 ? hi - 1 : k));
 }
 
+// ---- division by a loop-invariant divisor -----------------------------------------------------------
+// a / d where d is the same for every cell of the launch (an expression of scalar parameters and literals: grid
+// spacings, time steps): the generators hoist d and its correctly rounded reciprocal r = 1 / d out of the march loop
+// (DivInv, one IEEE division per thread) and every cell pays three FP instructions instead of the ~10-instruction
+// division sequence.  Markstein's theorem: with r = RN(1/d), q0 = RN(a r), e = a - q0 d (exact in one FMA), the value
+// q = RN(q0 + e r) IS the correctly rounded quotient RN(a / d) as long as nothing under- or overflows on the way; the
+// exponent-range guards below (on d once, on the result per cell) keep every intermediate normal, anything else — zeros,
+// infinities, NaNs, tiny or huge operands — takes the IEEE division.  Bit-for-bit equal to a / d: checked exhaustively
+// over all 2^23 significands for hundreds of divisors (tests/test_div_inv.py), and by every parity test that divides.
+template <class T>
+struct DivInv {
+  T d, r;   // r = RN(1 / d), or NaN when |d| is outside the guarded exponent range (every quotient then takes the IEEE path)
+};
+__device__ __noinline__ float div_ieee(float a, float d) { return a / d; }
+__device__ __noinline__ double div_ieee(double a, double d) { return a / d; }
+#ifdef B200_HOST_EMU
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline unsigned __float_as_uint(float v) { unsigned u; std::memcpy(&u, &v, 4); return u; }
+inline long long __double_as_longlong(double v) { long long u; std::memcpy(&u, &v, 8); return u; }
+#endif
+__device__ __forceinline__ DivInv<float> div_inv_make(float d) {
+  const unsigned m = __float_as_uint(d) * 2u - 0x61000000u;   // |d| in [2^-30, 2^30): exponent field, sign shifted out
+  return {d, m < 0x3c000000u ? 1.0f / d : __int_as_float(0x7fc00000)};
+}
+__device__ __forceinline__ DivInv<double> div_inv_make(double d) {
+  const unsigned long long m = (unsigned long long)__double_as_longlong(d) * 2ULL - 0x66e0000000000000ULL;   // |d| in [2^-200, 2^200)
+  return {d, m < 0x3200000000000000ULL ? 1.0 / d : __longlong_as_double(0x7ff8000000000000LL)};
+}
+// The quotient by Markstein's sequence; `bad` accumulates (unsigned max) the exponent-range test of every quotient of
+// a group, so that ONE compare + branch guards the whole group: if it fires, the group is redone with IEEE divisions.
+__device__ __forceinline__ float div_inv_try(float a, const DivInv<float>& v, unsigned& bad) {
+  const float q0 = __fmul_rn(a, v.r);
+  const float e = __fmaf_rn(-q0, v.d, a);
+  const float q = __fmaf_rn(e, v.r, q0);
+  const unsigned m = __float_as_uint(q) * 2u - 0x43000000u;   // < 0x78000000: |q| in [2^-60, 2^60) (a NaN, an infinity, a zero are outside)
+  bad = bad > m ? bad : m;
+  return q;
+}
+__device__ __forceinline__ bool div_inv_bad(unsigned bad) { return bad >= 0x78000000u; }
+__device__ __forceinline__ double div_inv_try(double a, const DivInv<double>& v, unsigned long long& bad) {
+  const double q0 = __dmul_rn(a, v.r);
+  const double e = __fma_rn(-q0, v.d, a);
+  const double q = __fma_rn(e, v.r, q0);
+  const unsigned long long m = (unsigned long long)__double_as_longlong(q) * 2ULL - 0x4160000000000000ULL;   // |q| in [2^-500, 2^500)
+  bad = bad > m ? bad : m;
+  return q;
+}
+__device__ __forceinline__ bool div_inv_bad(unsigned long long bad) { return bad >= 0x7d00000000000000ULL; }
+// single quotient (generators that do not group)
+__device__ __forceinline__ float div_inv(float a, const DivInv<float>& v) {
+  unsigned bad = 0u;
+  const float q = div_inv_try(a, v, bad);
+  return div_inv_bad(bad) ? div_ieee(a, v.d) : q;
+}
+__device__ __forceinline__ double div_inv(double a, const DivInv<double>& v) {
+  unsigned long long bad = 0ULL;
+  const double q = div_inv_try(a, v, bad);
+  return div_inv_bad(bad) ? div_ieee(a, v.d) : q;
+}
+
 // ---- NumPy-semantics helpers -------------------------------------------------------------------
 // np.minimum / np.maximum propagate NaN (fmin/fmax do not).
 __device__ __forceinline__ float min_(float a, float b) { return (isnan(a) || a < b) ? a : b; }

@@ -12,6 +12,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __restrict__
 #define __grid_constant__
 #define __launch_bounds__(...)

@@ -132,6 +132,8 @@ def test_thin_strip_schedule_composes_two_kernel_variants(tuned):
         {"interior_loop": True, "static_pitch": 160, "row_pointers": True}, {"static_pitch": 160, "row_pointers": True},
         {"interior_loop": "steady", "static_pitch": 160}, {"interior_loop": True, "static_pitch": 160, "tile_j": 52, "min_blocks": 8},
         {"interior_loop": True, "static_pitch": 192},  # pitch of the arguments differs -> general loop, same result
+        {"k_order": True}, {"k_order": False, "period": 8, "div_slow": "call"}, {"period": 4, "div_slow": "inline"}, {"div_inv": False},
+        {"interior_loop": True, "static_pitch": 160, "period": 8}, {"interior_loop": True, "static_pitch": 160, "k_order": True, "halo_wait": True},
     ],
 )  # fmt: skip
 def test_streaming_tuning_knobs_do_not_change_results(opts):
@@ -305,3 +307,18 @@ def test_halo_wait_kernels_put_the_boundary_tiles_last_and_wait_for_the_flags():
             es.run(got, params, domain, origins, layout="b200", guard="end", halo_wait=hw)
             np.testing.assert_array_equal(got["out_field"], ref["out_field"])
     assert "wait_flag" not in EmuStencil(st, {}, name="hdiff_plain").source
+
+
+@pytest.mark.parametrize("opts", [{}, {"k_order": False}, {"halo_wait": True}, {"interior_loop": True, "static_pitch": 160, "halo_wait": True},
+                                  {"tma": 2, "tile_j": 16, "interior_loop": True, "static_pitch": 160}])  # fmt: skip
+def test_level_fastest_task_order_of_kernels_that_read_at_k_offsets(opts):
+    """kernels with K-offset inputs take the LEVEL as the fastest task index (L1/L2 re-use of the planes read from three
+    levels); one- and two-level sections use short J tiles.  Same results, every task decoded exactly once."""
+    for name in ("fw_pgrad_f32", "fw_div_f32"):
+        st = testing.load_ir(name, "staged")
+        es = EmuStencil(st, {"strategy": "auto", **opts}, name=name + "_korder")
+        ks = [k for k in es.plan["kernels"] if k["kind"] == "stream"]
+        assert ks and (("task % nk" in es.source) == (opts.get("k_order", "auto") is not False))
+        if "tile_j" not in opts:
+            assert {k["tile"][1] for k in ks} == {8, 64}  # thin top / bottom sections, full-height middle section
+        run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(139, 150, 5), seed=3, layout="b200", guard="end")
