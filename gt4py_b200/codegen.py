@@ -535,14 +535,22 @@ class Generator:
         while n < len(loops):
             loop = loops[n]
             group = [loop]
-            if loop["order"] != "parallel" and not _needs_level_sync(loop) and self.opt.get("fuse_columns", False):
+            if loop["order"] != "parallel" and not _needs_level_sync(loop) and (self.opt.get("fuse_columns", False) or self.opt.get("col_smem", False)):
                 m = n + 1
                 while (m < len(loops) and loops[m]["order"] != "parallel" and not _needs_level_sync(loops[m])
                        and all(codegen_column.fusable(g, loops[m]) for g in group)):  # fmt: skip
                     group.append(loops[m])
                     m += 1
             if len(group) > 1:
-                k = codegen_column.try_emit(self, group, self.opt)
+                # fields of the loops outside this kernel: temporaries none of them touches may live in shared memory
+                external = {a["name"] for lp in self.st["loops"] if not any(lp is g for g in group)
+                            for sec in lp["sections"] for he in sec["hes"] for a in b2ir.field_accesses(he["body"])}  # fmt: skip
+                k = codegen_column.try_emit(self, group, self.opt, external)
+                if k is not None and not self.opt.get("fuse_columns", False) and not self.kernels[k].get("smem_fields"):
+                    # fused only for the sake of shared-memory temporaries and none qualified: keep the separate sweeps
+                    self.kernels.pop()
+                    self.src.pop()
+                    k = None
                 if k is not None:
                     self.steps.append({"t": "launch", "kernel": k})
                     n += len(group)
@@ -567,7 +575,7 @@ class Generator:
         ]
         source = "\n".join(header) + "\n\n".join(self.src) + "\n"
         plan = {
-            "version": 2,
+            "version": 3,
             "name": self.st["name"],
             "fields": [
                 {
@@ -635,7 +643,8 @@ def plan_to_text(plan: Dict[str, Any]) -> str:
         tile = k.get("tile", [k["block"][0], k["block"][1], 1])
         L.append(
             f"kernel {k['name']} {kind} {k['block'][0]} {k['block'][1]} {k['block'][2]} "
-            f"{tile[0]} {tile[1]} {tile[2]} {e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]} {b(k['k_lo'])} {b(k['k_hi'])} {k['smem']} {int(k.get('qshift', 0))}"
+            f"{tile[0]} {tile[1]} {tile[2]} {e[0][0]} {e[0][1]} {e[1][0]} {e[1][1]} {b(k['k_lo'])} {b(k['k_hi'])} {k['smem']} {int(k.get('qshift', 0))} "
+            f"{int(k.get('smem_per_k', 0))} {int(k.get('smem_kcap', 0))}"
         )
     L.append(f"ntmaps {len(plan.get('tmaps', []))}")
     for t in plan.get("tmaps", []):

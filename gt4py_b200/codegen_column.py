@@ -50,7 +50,7 @@ def _tag(key: Key) -> str:
 
 
 class ColumnKernel:
-    def __init__(self, gen, loops: List[dict], opts: Dict[str, Any]):
+    def __init__(self, gen, loops: List[dict], opts: Dict[str, Any], external: Optional[Set[str]] = None):
         from . import codegen as cg
 
         self.cg = cg
@@ -83,9 +83,51 @@ class ColumnKernel:
         # never deferred, so those reads always see the latest value
         self.direct_read: Set[str] = {a["name"] for a in acc if not a["write"] and isinstance(a["off"], dict)}
         self.div_hoisted: Dict[str, str] = {}
+        self.smem_fields: List[str] = self._smem_candidates(acc, external) if len(loops) > 1 and opts.get("col_smem", False) else []
+        self.smem_mode = False
         pf = opts.get("seq_prefetch", True)
         self.depth = max(0, int(pf)) if not isinstance(pf, bool) else (1 if pf else 0)  # levels of load look-ahead
         self.prefetch = self.depth > 0
+
+    def _smem_candidates(self, acc, external: Optional[Set[str]]) -> List[str]:
+        """Temporaries of fused sweeps that can live in SHARED memory instead of global scratch (`col_smem`): the
+        forward sweep of an implicit vertical solve hands its coefficients to the back substitution through temporaries
+        (`ccol`, `dcol`); when both sweeps run in the same thread and nothing else touches those temporaries, a column's
+        values are private to the thread from the first write to the last read: nK x 4 (8) bytes per thread and field,
+        indexed [k][thread] (conflict-free), never written to or re-read from HBM (fast-waves w solver: 48 -> 32 B/cell).
+        The b200 counterpart of GridTools' k-caches without fill / flush (gtc/gtcpp/gtcpp_codegen.py:229-232).
+        Conditions: a temporary no other kernel touches (`external` = fields of the loops outside this kernel), accessed
+        in its own column only, at constant K offsets that stay inside [0, nK) for every domain."""
+        if external is None:
+            return []
+        out = []
+        min_k = int(self.gen.st["domain_info"]["min_k"])
+        for name in sorted(self.cacheable):
+            d = self.ft.entries[self.ft.index[name]]
+            if d["kind"] != "temp" or name in external:
+                continue
+            mine = [a for a in acc if a["name"] == name]
+            if any(isinstance(a["off"], dict) or (a["off"][0], a["off"][1]) != (0, 0) or a.get("data_index") for a in mine):
+                continue
+            ok = True
+            for loop in self.loops:
+                for sec in loop["sections"]:
+                    (b0, o0), (b1, o1) = sec["interval"]
+                    for he in sec["hes"]:
+                        for a in b2ir.field_accesses(he["body"]):
+                            if a["name"] != name:
+                                continue
+                            dk = int(a["off"][2])
+                            # lowest level touched k0 + dk >= 0, highest k1 - 1 + dk <= nK - 1, for every domain the
+                            # stencil accepts (nK >= domain_info.min_k)
+                            if dk < 0 and not (o0 + dk >= 0 if b0 == "start" else min_k + o0 + dk >= 0):
+                                ok = False
+                            if dk > 0 and not (o1 + dk <= 0 if b1 == "end" else o1 + dk <= min_k):
+                                ok = False
+            if ok:
+                out.append(name)
+        # 8-byte fields first: every field's slice of the dynamic shared memory stays naturally aligned
+        return sorted(out, key=lambda n: (-b2ir.ITEMSIZE[self.ft.entries[self.ft.index[n]]["dtype"]], n))
 
     def _check_stmts(self, stmts) -> None:
         for s in stmts:
@@ -105,6 +147,8 @@ class ColumnKernel:
         if dj:
             off += f" + ({dj}) * {f}.s[1]"
         kk = f"({kexpr} + ({dk}))" if dk else kexpr
+        if self.smem_mode and name in self.smem_fields:
+            return f"s_{self.cg._cname(name)}[{kk} * {self.nthreads}]"
         return f"c_{self.cg._cname(name)}[(long long){kk} * {f}.s[2]{off}]"
 
     def _load(self, key: Key, kexpr: str) -> str:
@@ -259,6 +303,8 @@ class ColumnKernel:
                 # the cell loaded `depth` levels early must not be written by the levels in between
                 if name in self.loop_written and -self.depth <= dk * step < 0:
                     continue
+                if self.smem_mode and name in self.smem_fields:
+                    continue  # shared memory: no look-ahead pipeline needed
                 prefetched.append(key)
         return carried, prefetched
 
@@ -267,6 +313,9 @@ class ColumnKernel:
         cg, gen = self.cg, self.gen
         name = gen._kname("col")
         bx, by = gen.BLOCK_SEQ
+        if self.smem_fields:
+            bx, by = (int(x) for x in self.opts.get("col_smem_block", (32, 2)))  # small CTAs: occupancy in fine steps
+        self.nthreads = bx * by
         (ei0, ei1), (ej0, ej1) = self.extent
         L = [f'extern "C" __global__ void __launch_bounds__({bx * by}) {name}(const __grid_constant__ Args A) {{']
         w = L.append
@@ -279,6 +328,41 @@ class ColumnKernel:
             ct = CT[self.ft.entries[n]["dtype"]]
             const = "" if fname in self.written else "const "
             w(f"  {const}{ct}* const c_{cg._cname(fname)} = ({const}{ct}*)A.f[{n}].p + (long long)i * A.f[{n}].s[0] + (long long)j * A.f[{n}].s[1];")
+        per_k = sum(b2ir.ITEMSIZE[self.ft.entries[self.ft.index[n]]["dtype"]] for n in self.smem_fields) * self.nthreads
+        kcap = (int(self.opts.get("col_smem_kb", 56)) * 1024) // per_k if per_k else 0
+        if kcap < 4:
+            self.smem_fields, per_k, kcap = [], 0, 0
+        self.smem_per_k, self.smem_kcap = per_k, kcap
+        if self.smem_fields:
+            # columns short enough for the shared-memory budget of a CTA keep these temporaries on chip (the launcher
+            # requests smem_per_k x nK bytes under the same condition); taller ones take the global-scratch code below
+            w("  B200_DYN_SMEM(b200_dsm);")
+            w(f"  if (A.g.nK <= {kcap}) {{")
+            off = 0
+            for fname in self.smem_fields:
+                ct = CT[self.ft.entries[self.ft.index[fname]]["dtype"]]
+                w(f"    {ct}* const s_{cg._cname(fname)} = reinterpret_cast<{ct}*>(b200_dsm + (size_t)A.g.nK * {off}) + (threadIdx.y * {bx} + threadIdx.x);")
+                off += b2ir.ITEMSIZE[self.ft.entries[self.ft.index[fname]]["dtype"]] * self.nthreads
+            self.smem_mode = True
+            self._emit_sweeps(L)
+            self.smem_mode = False
+            w("    return;")
+            w("  }")
+        self._emit_sweeps(L)
+        w("}")
+        L[div_marker:div_marker] = [f"  const auto {nm} = b200::div_inv_make({cx});" for cx, nm in self.div_hoisted.items()]
+        gen.src.append("\n".join(L))
+        gen.live |= {a["name"] for he in self.hes for a in b2ir.field_accesses(he["body"])}
+        gen.kernels.append(
+            {"name": name, "kind": "seq", "block": [bx, by, 1], "extent": [list(self.extent[0]), list(self.extent[1])],
+             "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": self._smem_pad(), "smem_per_k": per_k, "smem_kcap": kcap,
+             "smem_fields": list(self.smem_fields)}
+        )  # fmt: skip
+        return len(gen.kernels) - 1
+
+    def _emit_sweeps(self, L: List[str]) -> None:
+        cg = self.cg
+        w = L.append
         for li, si, loop, sec in [(li, si, lp, sec) for li, lp in enumerate(self.loops) for si, sec in enumerate(lp["sections"])]:
             self.step = 1 if loop["order"] == "forward" else -1
             fwd = self.step == 1
@@ -324,15 +408,6 @@ class ColumnKernel:
             w("      }")
             w("    }")
             w("  }")
-        w("}")
-        L[div_marker:div_marker] = [f"  const auto {nm} = b200::div_inv_make({cx});" for cx, nm in self.div_hoisted.items()]
-        gen.src.append("\n".join(L))
-        gen.live |= {a["name"] for he in self.hes for a in b2ir.field_accesses(he["body"])}
-        gen.kernels.append(
-            {"name": name, "kind": "seq", "block": [bx, by, 1], "extent": [list(self.extent[0]), list(self.extent[1])],
-             "k_lo": ["start", 0], "k_hi": ["start", 1], "smem": self._smem_pad()}
-        )  # fmt: skip
-        return len(gen.kernels) - 1
 
     def _smem_pad(self) -> int:
         """`seq_smem_pad` = bytes of (unused) dynamic shared memory requested per CTA: caps the resident CTAs per SM
@@ -362,7 +437,7 @@ def fusable(a: dict, b: dict) -> bool:
     return not (wa & ob) and not (wb & oa)
 
 
-def try_emit(gen, loops, opts: Dict[str, Any]) -> Optional[int]:
+def try_emit(gen, loops, opts: Dict[str, Any], external: Optional[Set[str]] = None) -> Optional[int]:
     """Emit one or several consecutive FORWARD/BACKWARD loops (no level synchronisation needed) as ONE
     column kernel with register k-caches; returns the kernel index or None when the template does not apply."""
     if not opts.get("seq_cache", True):
@@ -370,6 +445,6 @@ def try_emit(gen, loops, opts: Dict[str, Any]) -> Optional[int]:
     if isinstance(loops, dict):
         loops = [loops]
     try:
-        return ColumnKernel(gen, list(loops), opts).emit()
+        return ColumnKernel(gen, list(loops), opts, external).emit()
     except NotColumnable:
         return None

@@ -205,6 +205,14 @@ __device__ __forceinline__ int clampk(long long k, int lo, int hi) {
   return (int)(k < lo ? lo : (k > hi - 1 ? hi - 1 : k));
 }
 
+// dynamic shared memory of a kernel (sized by the launcher); the CPU emulation runs the threads of a CTA one after the
+// other, each through the whole kernel, with a static buffer
+#ifndef B200_HOST_EMU
+#define B200_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else
+#define B200_DYN_SMEM(name) static unsigned char name[232448] __attribute__((aligned(16)))
+#endif
+
 // ---- division by a loop-invariant divisor -----------------------------------------------------------
 // a / d where d is the same for every cell of the launch (an expression of scalar parameters and literals: grid
 // spacings, time steps): the generators hoist d and its correctly rounded reciprocal r = 1 / d out of the march loop

@@ -86,6 +86,9 @@ struct KernelPlan {
   int ei0, ei1, ej0, ej1;
   Bound k_lo, k_hi;
   int smem;
+  // column kernels with temporaries in shared memory (codegen_column.py, col_smem): smem_per_k bytes of dynamic shared memory
+  // per level when the domain has at most smem_kcap levels (the kernel takes its global-scratch path otherwise)
+  int smem_per_k = 0, smem_kcap = 0;
   int qshift = 0;  // streaming kernels: segments may start up to this many vectors left of the first stored column
   cudaKernel_t fn = nullptr;
 };
@@ -148,7 +151,7 @@ int parse_plan(const char* text, b200_stencil* st) {
   std::istringstream in(text);
   std::string tok;
   int version = 0;
-  if (!(in >> tok >> version) || tok != "b200plan" || version != 2)
+  if (!(in >> tok >> version) || tok != "b200plan" || version != 3)
     return fail(B200_ERR_INVALID, "launch plan: bad header");
   int nfields = 0, nkernels = 0, nsteps = 0, ntmaps = 0;
   while (in >> tok) {
@@ -168,7 +171,7 @@ int parse_plan(const char* text, b200_stencil* st) {
     } else if (tok == "kernel") {
       KernelPlan k;
       in >> k.name >> k.kind >> k.block[0] >> k.block[1] >> k.block[2] >> k.tile[0] >> k.tile[1] >> k.tile[2] >>
-          k.ei0 >> k.ei1 >> k.ej0 >> k.ej1 >> k.k_lo.level >> k.k_lo.off >> k.k_hi.level >> k.k_hi.off >> k.smem >> k.qshift;
+          k.ei0 >> k.ei1 >> k.ej0 >> k.ej1 >> k.k_lo.level >> k.k_lo.off >> k.k_hi.level >> k.k_hi.off >> k.smem >> k.qshift >> k.smem_per_k >> k.smem_kcap;
       st->kernels.push_back(k);
     } else if (tok == "ntmaps") {
       in >> ntmaps;
@@ -354,7 +357,9 @@ int launch(b200_stencil* st, KernelPlan& k, std::vector<char>& blob, int k_lo, i
   }
   if (grid.y > 65535 || grid.z > 65535) return fail(B200_ERR_INVALID, "grid too large for kernel %s", k.name.c_str());
   void* params[1] = {blob.data()};
-  CU(cudaLaunchKernel((const void*)k.fn, grid, block, params, (size_t)k.smem, stream));
+  size_t smem = (size_t)k.smem;
+  if (k.smem_per_k > 0 && g->nK <= k.smem_kcap) smem += (size_t)k.smem_per_k * (size_t)g->nK;
+  CU(cudaLaunchKernel((const void*)k.fn, grid, block, params, smem, stream));
   return 1;
 }
 
@@ -401,8 +406,9 @@ int b200_stencil_load(const void* image, size_t image_size, const char* plan_tex
   }
   for (auto& k : st->kernels) {
     e = cudaLibraryGetKernel(&k.fn, st->lib, k.name.c_str());
-    if (e == cudaSuccess && k.smem > 48 * 1024)
-      e = cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem);
+    const int smem_max = k.smem + k.smem_per_k * k.smem_kcap;
+    if (e == cudaSuccess && smem_max > 48 * 1024)
+      e = cudaFuncSetAttribute((const void*)k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) {
       std::string kn = k.name;
       cudaLibraryUnload(st->lib);

@@ -148,7 +148,9 @@ SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lo
 
 @pytest.mark.parametrize("name", SEQ_CASES)
 @pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"seq_cache": False},
-                                  {"fuse_columns": True}, {"fuse_columns": True, "seq_prefetch": 2}])  # fmt: skip
+                                  {"fuse_columns": True}, {"fuse_columns": True, "seq_prefetch": 2},
+                                  {"col_smem": True}, {"col_smem": True, "seq_prefetch": 4}, {"col_smem": True, "col_smem_kb": 1}, {"col_smem": True, "col_smem_kb": 3},
+                                  {"col_smem": True, "col_smem_block": (64, 2), "fuse_columns": True, "div_inv": False}])  # fmt: skip
 def test_column_generator_variants(name, opts):
     """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
     baseline column kernel: same results on ragged domains, both lowerings"""
@@ -322,3 +324,22 @@ def test_level_fastest_task_order_of_kernels_that_read_at_k_offsets(opts):
         if "tile_j" not in opts:
             assert {k["tile"][1] for k in ks} == {8, 64}  # thin top / bottom sections, full-height middle section
         run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(139, 150, 5), seed=3, layout="b200", guard="end")
+
+
+def test_fused_sweeps_keep_their_private_temporaries_in_shared_memory():
+    """`col_smem`: the coefficients the forward sweep of the fast-waves w solver hands to its back substitution never
+    touch global memory (one kernel, dynamic shared memory sized by the launcher per level); a domain taller than the
+    shared-memory budget takes the global-scratch code of the same kernel."""
+    st = testing.load_ir("fw_wsolve_f32", "default")
+    es = EmuStencil(st, {"col_smem": True}, name="wsolve_smem")
+    (k,) = es.plan["kernels"]
+    assert k["smem_fields"] == ["ccol", "dcol"] and k["smem_per_k"] == 2 * 4 * 64 and k["smem_kcap"] == 112 and k["block"] == [32, 2, 1]
+    body = es.source[es.source.index("if (A.g.nK <= 112)"):es.source.index("return;\n  }")]
+    assert "s_ccol[" in body and "c_ccol[" not in body and "c_dcol[" not in body
+    from gt4py_b200 import codegen
+
+    assert f" {k['smem_per_k']} {k['smem_kcap']}\n" in codegen.plan_to_text(es.plan)  # what the launcher sizes the request from
+    # API fields another kernel does not see are not candidates: the Thomas solver's sup / rhs are outputs
+    assert not EmuStencil(testing.load_ir("tridiagonal_f64", "default"), {"col_smem": True}, name="tri_smem").plan["kernels"][0].get("smem_fields")
+    for domain in ((21, 6, 30), (5, 3, 130)):  # shared-memory path / fallback path (130 levels > 112)
+        run_emulated("fw_wsolve_f32", "default", {"col_smem": True}, domain=domain, seed=1, layout="b200", guard="end")

@@ -93,7 +93,7 @@ def test_fused_kernels_fit_a_cta():
 def test_occupancy_cap_option_is_validated_and_reaches_the_plan():
     st = testing.load_ir("tridiagonal_f64", "default")
     _src, plan = codegen.generate(st, {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 110 * 1024})
-    assert [k["smem"] for k in plan["kernels"]] == [110 * 1024] and " 112640 0\n" in codegen.plan_to_text(plan)  # (smem, then the segment-shift flag)
+    assert [k["smem"] for k in plan["kernels"]] == [110 * 1024] and " 112640 0 0 0\n" in codegen.plan_to_text(plan)  # (smem, the segment-shift flag, shared memory per level / level cap)
     _check(st, {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 110 * 1024}, "tridiagonal_f64_default")
     with pytest.raises(ValueError, match="seq_smem_pad"):
         codegen.generate(st, {"seq_smem_pad": 300 * 1024})

@@ -18,6 +18,9 @@ WORKLOADS = {
     "upwind5": ("upwind5_f32", "staged", (2048, 2048, 80)),
     "pgrad": ("fw_pgrad_f32", "staged", (4096, 512, 80)),
     "div": ("fw_div_f32", "staged", (4096, 512, 80)),
+    "wsolve": ("fw_wsolve_f32", "default", (4096, 512, 80)),
+    "tridiagonal": ("tridiagonal_f64", "default", (512, 512, 160)),
+    "vadv": ("vadv_f64", "default", (512, 512, 160)),
 }
 P = {"interior_loop": True, "static_pitch": "auto"}
 U = dict(P)  # (uniform_task is the default now; {"uniform_task": False} = the round-1 addressing)
@@ -34,6 +37,15 @@ CANDIDATES = [
 ]
 
 
+def candidates_for(workload: str):
+    """--candidates FILE: JSON {workload or "*": [options, ...]} replaces the built-in list (session-specific sweeps)."""
+    for n, arg in enumerate(sys.argv):
+        if arg == "--candidates":
+            table = json.loads(pathlib.Path(sys.argv[n + 1]).read_text())
+            return table.get(workload, table.get("*", []))
+    return CANDIDATES
+
+
 def precompile():
     """Build container: AOT-compile every candidate into the in-tree cubin cache (travels with gpurun)."""
     import math
@@ -46,7 +58,7 @@ def precompile():
         st = testing.load_ir(name, variant)
         shapes, _ = testing.field_layout(st, domain)
         widths = {math.ceil(s[0] / 32) * 32 for s in shapes.values() if len(s) == 3}
-        for cand in CANDIDATES:
+        for cand in candidates_for(wl):
             cand = dict(cand)
             if cand.get("static_pitch") == "auto":
                 if len(widths) != 1:
@@ -81,6 +93,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="hdiff")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--candidates", default=None)
     a = ap.parse_args()
     peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
     for wl in WORKLOADS if a.workload == "all" else a.workload.split(","):
@@ -89,7 +102,7 @@ def main():
         fields, params, origins, domain = testing.make_case_data(st, name, domain=domain, seed=0)
         dev = {k: (storage.from_array(v, aligned_index=origins[k]) if v is not None else None) for k, v in fields.items()}
         s = B200Stencil(st, {"strategy": "auto", "device_sync": False})
-        res = s.autotune(dev, params, domain=domain, origin=origins, iters=a.iters, candidates=CANDIDATES, refine=0)
+        res = s.autotune(dev, params, domain=domain, origin=origins, iters=a.iters, candidates=candidates_for(wl), refine=0)
         bpc = testing.algorithmic_bytes_per_cell(st)
         cells = domain[0] * domain[1] * domain[2]
         for cand, ms in res:

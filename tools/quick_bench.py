@@ -27,7 +27,17 @@ def bench(name, variant, strategy, domain, iters=20, warm=5, extra=None):
             "mcells_s": round(cells/ms/1e3,1), "gbs": round(cells*bpc/ms/1e6,1), "launches": s.compiled.last_launches, **(extra or {})}
 
 if __name__ == "__main__":
-    ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); ap.add_argument("--only", default=None); ap.add_argument("--name", default="hdiff_f32"); ap.add_argument("--variant", default="staged"); ap.add_argument("--domain", default="1024,1024,80"); ap.add_argument("--iters", type=int, default=20); a = ap.parse_args()
+    ap = argparse.ArgumentParser(); ap.add_argument("--cases", default="all"); ap.add_argument("--only", default=None); ap.add_argument("--name", default="hdiff_f32"); ap.add_argument("--variant", default="staged"); ap.add_argument("--domain", default="1024,1024,80"); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--candidates", default=None, help="JSON list of option dicts: one line per variant of --name"); a = ap.parse_args()
+    if a.candidates is not None:
+        pk = json.loads((pathlib.Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]
+        for cand in json.loads(a.candidates):
+            try:
+                r = bench(a.name, a.variant, "auto", tuple(int(x) for x in a.domain.split(",")), iters=a.iters, extra=cand)
+                r["frac_of_peak"] = round(r["gbs"] / pk, 4)
+                print(json.dumps(r), flush=True)
+            except Exception as e:
+                print(json.dumps({"name": a.name, "options": cand, "error": repr(e)[:300]}), flush=True)
+        sys.exit(0)
     if a.only is not None:
         print(json.dumps(bench(a.name, a.variant, "auto", tuple(int(x) for x in a.domain.split(",")), iters=a.iters, extra=json.loads(a.only)))); sys.exit(0)
     H=("hdiff_f32","staged","auto",(1024,1024,80))
