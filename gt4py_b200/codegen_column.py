@@ -68,6 +68,7 @@ class ColumnKernel:
         self.extent = ext
         acc = [a for he in self.hes for a in b2ir.field_accesses(he["body"])]
         self.written: Set[str] = {a["name"] for a in acc if a["write"]}
+        self.read: Set[str] = {a["name"] for a in acc if not a["write"]}
         self.loop_written: Set[str] = set(self.written)  # fields written by the sweep being emitted
         for a in acc:
             if a["write"] and (isinstance(a["off"], dict) or tuple(a["off"]) != (0, 0, 0)):
@@ -85,6 +86,8 @@ class ColumnKernel:
         self.div_hoisted: Dict[str, str] = {}
         self.smem_fields: List[str] = self._smem_candidates(acc, external) if len(loops) > 1 and opts.get("col_smem", False) else []
         self.smem_mode = False
+        self._slot: Optional[int] = None
+        self._ring: Set[Key] = set()
         pf = opts.get("seq_prefetch", True)
         self.depth = max(0, int(pf)) if not isinstance(pf, bool) else (1 if pf else 0)  # levels of load look-ahead
         self.prefetch = self.depth > 0
@@ -156,7 +159,25 @@ class ColumnKernel:
         if name in self.written:
             return self._addr(key, kexpr)
         ct = CT[self.ft.entries[self.ft.index[name]]["dtype"]]
+        if self.opts.get("col_hints", False) and ct in ("float", "double", "int", "long long"):
+            # read once by this kernel: streaming (evict-first) load, so that the lines the back substitution re-reads
+            # (the forward sweep's own stores) are what stays in L2
+            return f"__ldcs(&{self._addr(key, kexpr)})"
         return f"b200::ldro<{ct}>(&{self._addr(key, kexpr)})"
+
+    def _store(self, key: Key, var: str) -> str:
+        name = key[0]
+        if self.opts.get("col_hints", False) and name not in self.read and not (self.smem_mode and name in self.smem_fields) \
+                and self._ctype(key) in ("float", "double", "int", "long long"):
+            return f"__stcs(&{self._addr(key, 'k')}, {var});"  # written, never read back here: streaming store
+        return f"{self._addr(key, 'k')} = {var};"
+
+    def _r(self, key: Key) -> str:
+        """Register of a column value.  Prefetched keys live in a ring of D + 1 registers: the copy of the level loop
+        that is being emitted (`self._slot`) consumes its own slot (no moves between the slots, see _emit_sweeps)."""
+        if self._slot is not None and key in self._ring:
+            return f"q{self._slot}_{_tag(key)}"
+        return f"r_{_tag(key)}"
 
     def _ctype(self, key: Key) -> str:
         return CT[self.ft.entries[self.ft.index[key[0]]]["dtype"]]
@@ -187,7 +208,7 @@ class ColumnKernel:
                 if isinstance(off, dict) or node.get("data_index") or name not in kern.cacheable:
                     return super().field_load(node)
                 key = (name, int(off[0]), int(off[1]), int(off[2]))
-                var = f"r_{_tag(key)}"
+                var = kern._r(key)
                 if key not in valid:
                     self.pre.append(f"{var} = {kern._load(key, 'k')};")
                     valid.add(key)
@@ -217,7 +238,7 @@ class ColumnKernel:
                     ct = CT[kern.ft.entries[kern.ft.index[name]]["dtype"]]
                     if name in kern.cacheable and not left.get("data_index"):
                         key = (name, 0, 0, 0)
-                        var = f"r_{_tag(key)}"
+                        var = kern._r(key)
                         flush(ind)
                         L.append(f"{ind}{var} = ({ct})({rhs});")
                         # an unconditional write makes every store of this level to the cell but the
@@ -225,7 +246,7 @@ class ColumnKernel:
                         if depth[0] == 0 and name not in kern.direct_read:
                             pending[key] = True
                         if key not in pending:
-                            L.append(f"{ind}{kern._addr(key, 'k')} = {var};")
+                            L.append(f"{ind}{kern._store(key, var)}")
                         # inside a branch a first definition is valid until the branch ends (dropped
                         # there); a key that was valid before stays valid on both paths
                         valid.add(key)
@@ -272,7 +293,7 @@ class ColumnKernel:
             L.append("      }")
             eg.locals = saved
         for key in pending:
-            L.append(f"      {kern._addr(key, 'k')} = r_{_tag(key)};")
+            L.append(f"      {kern._store(key, kern._r(key))}")
         return L, exposed, valid, touched
 
     # ---- per-section plan ------------------------------------------------------------------------
@@ -375,14 +396,58 @@ class ColumnKernel:
             w(f"  {{  // {loop['order']} sweep {li}, section {si}: carried {[_tag(c) for c in carried]}, prefetched {[_tag(p) for p in prefetched]}")
             w(f"    const int k0 = {k0}, k1 = {k1};")
             w("    if (k0 < k1) {")
-            for key in sorted(touched | live):
-                w(f"      {self._ctype(key)} r_{_tag(key)};")
             first = "k0" if fwd else "(k1 - 1)"
             D = self.depth
 
             def ahead(base: str, n: int) -> str:  # level n march steps after `base`, clamped to the section
                 return f"(({base}) + {n} < k1 ? ({base}) + {n} : k1 - 1)" if fwd else f"(({base}) - {n} >= k0 ? ({base}) - {n} : k0)"
 
+            def rotations(final_keys):
+                # rotate the carried registers towards the next level (sources still hold this level)
+                for key in sorted(carried, key=lambda c: c[3] * self.step):
+                    src = (key[0], key[1], key[2], key[3] + self.step)
+                    if src not in final_keys and src not in carried:
+                        raise NotColumnable("carry chain")  # pragma: no cover
+                    w(f"      {self._r(key)} = {self._r(src)};")
+
+            if prefetched and self.opts.get("seq_rotate", True):
+                # look-ahead WITHOUT register moves: the prefetched values live in a ring of S = D + 1 registers and
+                # the level loop is unrolled S times; copy u consumes slot u and, at its top, issues the loads of the
+                # level D steps ahead into the slot the previous copy has just consumed.  (A shifting pipeline
+                # `r = p1; p1 = p2; ...; p(D-1) = n` makes every level wait for the load issued ONE level earlier — the
+                # move needs its source — so its depth never exceeded one: profiles/README.md r02n, the stall sites
+                # of the w solver are those moves.)
+                S = D + 1
+                self._ring = set(prefetched)
+                for key in sorted((touched | live) - self._ring):
+                    w(f"      {self._ctype(key)} r_{_tag(key)};")
+                for key in prefetched:
+                    w(f"      {self._ctype(key)} " + ", ".join(f"q{u}_{_tag(key)}" for u in range(S)) + ";")
+                for key in sorted(live - self._ring):
+                    w(f"      r_{_tag(key)} = {self._load(key, first)};")
+                for u in range(D):
+                    for key in prefetched:
+                        w(f"      q{u}_{_tag(key)} = {self._load(key, ahead(first, u) if u else first)};")
+                w(f"      for (int kb = k0; kb < k1; kb += {S}) {{" if fwd else f"      for (int kb = k1 - 1; kb >= k0; kb -= {S}) {{")
+                for u in range(S):
+                    self._slot = u
+                    body_u, _exp, final_u, _t = self._emit_level(sec, live)
+                    w(f"      {{ const int k = kb {'+' if fwd else '-'} {u};   // ring slot {u}")
+                    w("      if (k < k1) {" if fwd else "      if (k >= k0) {")
+                    w(f"      const int kn = {ahead('k', D)};")
+                    for key in prefetched:
+                        w(f"      q{(u + D) % S}_{_tag(key)} = {self._load(key, 'kn')};")
+                    L.extend(body_u)
+                    rotations(final_u)
+                    w("      }}")
+                self._slot = None
+                self._ring = set()
+                w("      }")
+                w("    }")
+                w("  }")
+                continue
+            for key in sorted(touched | live):
+                w(f"      {self._ctype(key)} r_{_tag(key)};")
             for key in sorted(live):
                 w(f"      r_{_tag(key)} = {self._load(key, first)};")
             for key in prefetched:  # look-ahead pipeline: p<j> holds the value of the level j steps ahead
@@ -394,13 +459,7 @@ class ColumnKernel:
                 for key in prefetched:
                     w(f"      const {self._ctype(key)} n_{_tag(key)} = {self._load(key, 'kn')};")
             L.extend(body)
-            # rotate the carried registers towards the next level (sources still hold this level)
-            order = sorted(carried, key=lambda c: c[3] * self.step)
-            for key in order:
-                src = (key[0], key[1], key[2], key[3] + self.step)
-                if src not in final and src not in carried:
-                    raise NotColumnable("carry chain")  # pragma: no cover
-                w(f"      r_{_tag(key)} = r_{_tag(src)};")
+            rotations(final)
             for key in prefetched:
                 chain = [f"r_{_tag(key)}"] + [f"p{j}_{_tag(key)}" for j in range(1, D)] + [f"n_{_tag(key)}"]
                 for dst, src in zip(chain, chain[1:]):

@@ -65,7 +65,9 @@ class StreamKernel:
         self.interval = interval
         self.hes = hes
         self.global_fields = global_fields  # temporaries that other kernels touch
-        self.opts = opts
+        (b0, o0), (b1, o1) = interval
+        self.thin = b0 == b1 and 0 < o1 - o0 <= 2  # a section of one or two levels: few, short tasks; no shared-memory ring
+        self.opts = {k: v for k, v in opts.items() if k not in ("tma", "min_blocks")} if self.thin else opts
         self.values: List[Value] = []
         self.vmap: Dict[Tuple, Value] = {}
         self.cur: Dict[str, Value] = {}
@@ -306,9 +308,8 @@ class StreamKernel:
         self.TJ = int(self.opts.get("tile_j", 64))
         # a section of one or two levels (the top / bottom level of a K-dependent computation) has few tasks: shorter J
         # tiles, or its launch is a fraction of a wave of warps that each march 64 rows (75 us for one 4096 x 512 plane)
-        (b0, o0), (b1, o1) = self.interval
-        if b0 == b1 and 0 < o1 - o0 <= 2 and "tile_j" not in self.opts:
-            self.TJ = 8
+        if self.thin:
+            self.TJ = int(self.opts.get("thin_tile_j", 8))
         self.NW = int(self.opts.get("warps", 4))
 
     def _pf(self) -> int:
@@ -493,10 +494,13 @@ class StreamKernel:
             w("      __syncwarp();")
             w("    }")
             w("  }")
+        # window registers start at ONE, not zero: rows and lanes outside the tile are never loaded, whatever is computed
+        # from them is never stored, but a zero dividend would send the warp's quotient group through the IEEE fallback
+        # (upwind5: 17 % of all executed instructions were fallback divisions of prologue rows, profiles/README.md r02n)
         for v in self.values:
             ct = CT[v.dtype]
             for s in range(v.window):
-                w("  " + f"{ct} " + ", ".join(f"{self.reg(v, s, e)} = ({ct})0" for e in range(V)) + ";")
+                w("  " + f"{ct} " + ", ".join(f"{self.reg(v, s, e)} = ({ct})1" for e in range(V)) + ";")
         self.row_guard: Dict[str, bool] = {}
         for v in self.values:
             if v.kind == "in" or v.store:
@@ -968,6 +972,7 @@ class StreamKernel:
                 # NaN, tiny, huge) -> the IEEE division for all of them, the same values where the fast path was valid
                 cond = " || ".join(f"b200::div_inv_bad({acc})" for acc in sorted({q[3] for q in group}))
                 L.append(ind2 + f"if (__builtin_expect(__any_sync(0xffffffffu, {cond}), 0)) {{")
+                L.append(ind2 + "  B200_TRACE(6);")
                 for nm, dv, ct, acc in group:
                     # (out-of-line: a call per quotient keeps the loop small but its ABI costs registers once the loop is
                     #  unrolled 4+ times — 71 / 96 / 108 for upwind5 at period 2 / 4 / 8 — hence inline there)

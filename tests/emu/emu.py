@@ -76,8 +76,8 @@ class EmuStencil:
 
     def trace(self, reset=True):
         """B200_TRACE counters: {0: steady-loop trips (pure), 1: steady-loop trips (edge/fastall),
-        2: general march steps, 3: steady-loop trips (interior), 4: interior prologue/epilogue steps} of the streaming kernels since the last reset."""
-        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(6)}
+        2: general march steps, 3: steady-loop trips (interior), 4: interior prologue/epilogue steps, 6: quotient groups redone by IEEE division (per lane)} of the streaming kernels since the last reset."""
+        return {slot: int(self.lib.emu_trace_read(slot, int(reset))) for slot in range(8)}
 
     # ---- mirror of launcher.cu ------------------------------------------------------------------
     def _temp_layout(self, f, dom):

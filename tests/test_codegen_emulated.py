@@ -149,7 +149,8 @@ SEQ_CASES = ["tridiagonal_f64", "vadv_f64", "fw_wsolve_f32", "fwd_scan_f64", "lo
 @pytest.mark.parametrize("name", SEQ_CASES)
 @pytest.mark.parametrize("opts", [{}, {"seq_prefetch": False}, {"seq_prefetch": 2}, {"seq_prefetch": 3}, {"seq_cache": False},
                                   {"fuse_columns": True}, {"fuse_columns": True, "seq_prefetch": 2},
-                                  {"col_smem": True}, {"col_smem": True, "seq_prefetch": 4}, {"col_smem": True, "col_smem_kb": 1}, {"col_smem": True, "col_smem_kb": 3},
+                                  {"col_smem": True}, {"col_smem": True, "seq_prefetch": 4}, {"col_smem": True, "col_smem_kb": 1}, {"col_smem": True, "col_smem_kb": 3}, {"seq_rotate": False, "seq_prefetch": 3},
+                                  {"fuse_columns": True, "seq_prefetch": 5, "col_hints": True}, {"col_hints": True, "seq_prefetch": 2},
                                   {"col_smem": True, "col_smem_block": (64, 2), "fuse_columns": True, "div_inv": False}])  # fmt: skip
 def test_column_generator_variants(name, opts):
     """register k-cache column kernels (default), without the one-level-ahead prefetch, and the
@@ -171,8 +172,12 @@ def test_column_generator_keeps_the_k_dataflow_in_registers():
     assert len(codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {})[1]["kernels"]) == 2  # default: one per sweep
     loop = sweep[sweep.index("for (int k"):]
     assert "carried ['sup_p0p0m1', 'rhs_p0p0m1']" in sweep
-    assert loop.count("b200::ldro<double>") == 2 and loop.count("= c_sup[") == 1 and loop.count("= c_rhs[") == 1
-    assert loop.count("c_sup[(long long)k *") == 1 and loop.count("c_rhs[(long long)k *") == 1  # one store each
+    # look-ahead of one level = a ring of two registers per prefetched value, the level loop unrolled twice, no moves
+    assert loop.count("// ring slot") == 2 and "q1_inf_p0p0p0 = b200::ldro<double>" in loop and "= q1_inf" not in loop and "= q0_inf" not in loop
+    assert loop.count("b200::ldro<double>") == 2 * 2 and loop.count("= c_sup[") == 2 and loop.count("= c_rhs[") == 2
+    assert loop.count("c_sup[(long long)k *") == 2 and loop.count("c_rhs[(long long)k *") == 2  # one store each per copy
+    old = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {"fuse_columns": True, "seq_rotate": False})[0]
+    assert "// ring slot" not in old and "n_inf_p0p0p0" in old  # the shifting pipeline stays available for comparison
     assert "(k + (-1))" not in loop
 
 
@@ -321,8 +326,8 @@ def test_level_fastest_task_order_of_kernels_that_read_at_k_offsets(opts):
         es = EmuStencil(st, {"strategy": "auto", **opts}, name=name + "_korder")
         ks = [k for k in es.plan["kernels"] if k["kind"] == "stream"]
         assert ks and (("task % nk" in es.source) == (opts.get("k_order", "auto") is not False))
-        if "tile_j" not in opts:
-            assert {k["tile"][1] for k in ks} == {8, 64}  # thin top / bottom sections, full-height middle section
+        assert {k["tile"][1] for k in ks} == {8, opts.get("tile_j", 64)}  # thin top / bottom sections, full-height middle section
+        assert not any(k["tma"] for k in ks if k["tile"][1] == 8)  # no shared-memory ring for the thin sections
         run_emulated(name, "staged", {"strategy": "auto", **opts}, domain=(139, 150, 5), seed=3, layout="b200", guard="end")
 
 
@@ -343,3 +348,26 @@ def test_fused_sweeps_keep_their_private_temporaries_in_shared_memory():
     assert not EmuStencil(testing.load_ir("tridiagonal_f64", "default"), {"col_smem": True}, name="tri_smem").plan["kernels"][0].get("smem_fields")
     for domain in ((21, 6, 30), (5, 3, 130)):  # shared-memory path / fallback path (130 levels > 112)
         run_emulated("fw_wsolve_f32", "default", {"col_smem": True}, domain=domain, seed=1, layout="b200", guard="end")
+
+
+def test_divisions_by_launch_invariants_take_the_reciprocal_path():
+    """upwind5 divides by 60*dx, 60*dy: the hoisted-reciprocal sequence must be what runs — also in the prologue rows and the
+    out-of-domain lanes of a tile (window registers start at one: a zero dividend would send the group to the IEEE
+    fallback) — and the fallback must still give the reference's bits when a field holds zeros / infinities."""
+    es = run_emulated("upwind5_f32", "staged", {"interior_loop": True, "static_pitch": 160}, domain=(139, 70, 2), seed=5, layout="b200", guard="end")
+    assert "b200::div_inv_try(" in es.source and "dv1 = b200::div_inv_make(" in es.source
+    tr = es.trace()
+    assert tr[3] > 0 and tr[6] == 0, tr
+    st = testing.load_ir("upwind5_f32", "staged")
+    fields, params, origins, domain = testing.make_case_data(st, "upwind5_f32", domain=(75, 41, 2), seed=3)
+    fields["u"][5:40, 7:20, :] = 0.0
+    fields["u"][50, 30, 1] = -0.0
+    fields["v"][20:30, 3:9, 0] = np.inf
+    fields["v"][60, 8, 1] = 1e-44  # subnormal
+    ref = {k: v.copy() for k, v in fields.items()}
+    numpy_oracle.run(st, ref, params, domain, origins)
+    es = EmuStencil(st, {"strategy": "auto"}, name="upwind5_specials")
+    got = {k: v.copy() for k, v in fields.items()}
+    es.run(got, params, domain, origins, layout="b200", guard="end")
+    assert es.trace()[6] > 0
+    np.testing.assert_array_equal(got["out"].view(np.uint32), ref["out"].view(np.uint32))  # bits, signed zeros and NaNs included
