@@ -50,6 +50,8 @@ def _tag(key: Key) -> str:
 
 
 class ColumnKernel:
+    RING_DEPTH = 3  # default look-ahead (levels) of the register ring
+
     def __init__(self, gen, loops: List[dict], opts: Dict[str, Any], external: Optional[Set[str]] = None):
         from . import codegen as cg
 
@@ -89,7 +91,9 @@ class ColumnKernel:
         self._slot: Optional[int] = None
         self._ring: Set[Key] = set()
         pf = opts.get("seq_prefetch", True)
-        self.depth = max(0, int(pf)) if not isinstance(pf, bool) else (1 if pf else 0)  # levels of load look-ahead
+        #: levels of load look-ahead (explicit), or None: 1 for the shifting pipeline, RING_DEPTH for the register ring
+        self.depth_opt: Optional[int] = None if pf is True else (0 if pf is False else max(0, int(pf)))
+        self.depth = 1 if self.depth_opt is None else self.depth_opt
         self.prefetch = self.depth > 0
 
     def _smem_candidates(self, acc, external: Optional[Set[str]]) -> List[str]:
@@ -388,7 +392,16 @@ class ColumnKernel:
             self.step = 1 if loop["order"] == "forward" else -1
             fwd = self.step == 1
             self.loop_written = {a["name"] for sc in loop["sections"] for he in sc["hes"] for a in b2ir.field_accesses(he["body"]) if a["write"]}
+            # which look-ahead pipeline (see below): planned at the ring's depth first (the hazard window of a look-ahead load
+            # grows with the depth), re-planned at depth 1 when the section keeps the shifting pipeline
+            rotate = self.opts.get("seq_rotate", "auto")
+            self.depth = self.depth_opt if self.depth_opt is not None else self.RING_DEPTH
             carried, prefetched = self._plan_section(sec)
+            if rotate == "auto":
+                rotate = not any(key[0] in self.loop_written for key in prefetched)
+            if not rotate and self.depth_opt is None:
+                self.depth = 1
+                carried, prefetched = self._plan_section(sec)
             live = set(carried) | set(prefetched)
             body, exposed, final, touched = self._emit_level(sec, live)
             k0 = cg._bound(sec["interval"][0], "A.g.nK")
@@ -397,7 +410,6 @@ class ColumnKernel:
             w(f"    const int k0 = {k0}, k1 = {k1};")
             w("    if (k0 < k1) {")
             first = "k0" if fwd else "(k1 - 1)"
-            D = self.depth
 
             def ahead(base: str, n: int) -> str:  # level n march steps after `base`, clamped to the section
                 return f"(({base}) + {n} < k1 ? ({base}) + {n} : k1 - 1)" if fwd else f"(({base}) - {n} >= k0 ? ({base}) - {n} : k0)"
@@ -410,7 +422,12 @@ class ColumnKernel:
                         raise NotColumnable("carry chain")  # pragma: no cover
                     w(f"      {self._r(key)} = {self._r(src)};")
 
-            if prefetched and self.opts.get("seq_rotate", True):
+            # which pipeline: the ring for sweeps whose look-ahead loads are pure inputs (fast-waves w solver 1.53 -> 1.35 ms,
+            # vadv 0.72 -> 0.65 ms at depth 3-4).  A sweep that updates its inputs in place (Thomas forward elimination:
+            # sup, rhs) already runs at the HBM roofline of its actual traffic with one level of look-ahead, its warps
+            # in step — there the ring only loosens the access pattern (0.470 -> 0.519 ms): it keeps the shifting form.
+            D = self.depth
+            if prefetched and rotate and D > 0:
                 # look-ahead WITHOUT register moves: the prefetched values live in a ring of S = D + 1 registers and
                 # the level loop is unrolled S times; copy u consumes slot u and, at its top, issues the loads of the
                 # level D steps ahead into the slot the previous copy has just consumed.  (A shifting pipeline

@@ -315,7 +315,13 @@ class StreamKernel:
     def _pf(self) -> int:
         """Extra window rows of the input streams (loads issued that many march steps before first use).  The
         bulk-async variant (`tma`) needs none: its look-ahead lives in the shared-memory ring, not in registers."""
-        return int(self.opts.get("prefetch", 0 if self.opts.get("tma") else 1))
+        if "prefetch" in self.opts:
+            return int(self.opts["prefetch"])
+        # one extra row per input stream pays while the streams are few (hdiff 2, upwind5 3: 0.73 -> 0.83 of the HBM peak in
+        # round 1); a kernel that streams many inputs (pressure gradient: 9 row streams, divergence: 6) is short of
+        # registers instead — 90 registers, 1.18 ms with the extra rows, 1.03 ms without (profiles/README.md r02o)
+        n_in = sum(1 for v in self.values if v.kind == "in")
+        return 0 if (self.opts.get("tma") or n_in > 4) else 1
 
     def _choose_windows(self) -> None:
         """Pick the rotation period U and the final register-window sizes.

@@ -172,12 +172,17 @@ def test_column_generator_keeps_the_k_dataflow_in_registers():
     assert len(codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {})[1]["kernels"]) == 2  # default: one per sweep
     loop = sweep[sweep.index("for (int k"):]
     assert "carried ['sup_p0p0m1', 'rhs_p0p0m1']" in sweep
-    # look-ahead of one level = a ring of two registers per prefetched value, the level loop unrolled twice, no moves
-    assert loop.count("// ring slot") == 2 and "q1_inf_p0p0p0 = b200::ldro<double>" in loop and "= q1_inf" not in loop and "= q0_inf" not in loop
-    assert loop.count("b200::ldro<double>") == 2 * 2 and loop.count("= c_sup[") == 2 and loop.count("= c_rhs[") == 2
-    assert loop.count("c_sup[(long long)k *") == 2 and loop.count("c_rhs[(long long)k *") == 2  # one store each per copy
-    old = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {"fuse_columns": True, "seq_rotate": False})[0]
-    assert "// ring slot" not in old and "n_inf_p0p0p0" in old  # the shifting pipeline stays available for comparison
+    # the forward elimination updates sup / rhs in place: shifting pipeline, one level of look-ahead (see codegen_column.py)
+    assert "// ring slot" not in loop and "n_inf_p0p0p0" in loop
+    assert loop.count("b200::ldro<double>") == 2 and loop.count("= c_sup[") == 1 and loop.count("= c_rhs[") == 1
+    assert loop.count("c_sup[(long long)k *") == 1 and loop.count("c_rhs[(long long)k *") == 1  # one store each
+    # the back substitution only reads what it looks ahead for: a ring of 3 + 1 registers per value, the level loop
+    # unrolled four times, no moves between the slots
+    back = src[src.index("backward sweep 1, section 1"):]
+    assert back.count("// ring slot") == 4 and "q3_sup_p0p0p0 = c_sup[" in back and "= q1_sup" not in back.replace("* q1_sup", "")
+    ring = codegen.generate(testing.load_ir("tridiagonal_f64", "default"), {"fuse_columns": True, "seq_rotate": True, "seq_prefetch": 1})[0]
+    fwd = ring[ring.index("forward sweep 0, section 1"):ring.index("backward sweep 1, section 0")]
+    assert fwd.count("// ring slot") == 2 and "q1_inf_p0p0p0 = b200::ldro<double>" in fwd and "= q1_inf" not in fwd
     assert "(k + (-1))" not in loop
 
 

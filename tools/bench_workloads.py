@@ -152,6 +152,16 @@ def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
             "sample": f"oracle, {sample[0]}x{sample[1]}x{sample[2]} sub-domain, {len(times)} steps, median ({os.cpu_count()} host cores available, NumPy uses 1)"}  # fmt: skip
 
 
+P = {"interior_loop": True, "static_pitch": "auto"}
+#: what --tune tries per stencil (a compact list: the winners of the round-2 sweeps, profiles/README.md)
+TUNE_CANDIDATES = (
+    {}, dict(P), {**P, "warps": 2}, {**P, "tile_j": 32}, {**P, "tile_j": 128}, {**P, "l2_prefetch": 1}, {**P, "prefetch": 0}, {**P, "prefetch": 1},
+    {**P, "tma": 3, "tile_j": 32, "prefetch": 0}, {**P, "tma": 3, "tile_j": 32, "prefetch": 0, "tma_mode": "bulk"},
+    {**P, "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk"}, {**P, "tma": 3, "tile_j": 16, "prefetch": 1, "tma_mode": "bulk"},
+    {**P, "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk", "stcs": True},
+)  # fmt: skip
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", required=True, choices=["tridiagonal", "upwind5", "fastwaves", "hdiff_x2"])
@@ -162,6 +172,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--plan", action="store_true")
     ap.add_argument("--options", default="{}", help="JSON code-generation options for every stencil")
+    ap.add_argument("--tune", action="store_true", help="N=1: autotune every stencil that can be re-run (B200Stencil.autotune over TUNE_CANDIDATES, "
+                    "each candidate validated bit for bit against the default variant) before the timed steps")
     ap.add_argument("--shrink", type=int, default=1, help="divide the horizontal domain by this factor (smoke runs only)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
@@ -225,6 +237,13 @@ def main():
         if peer is not None and k in w["exchanges"]:
             sopts["halo_wait"] = True
         st = B200Stencil(s["ir"], sopts, name=f"{s['fixture']}.{s['variant']}")
+        if args.tune and world == 1:
+            try:
+                tuned = st.autotune({p: sets[0][b] for p, b in s["binding"].items()}, default_params(s["ir"], s["fixture"]), domain=(ni, nj, nk),
+                                    origin={p: origin3 for p in s["binding"]}, candidates=TUNE_CANDIDATES, iters=10, refine=2)  # fmt: skip
+                s["tuned"] = {"options": tuned[0][0], "ms": tuned[0][1], "candidates": len(tuned)}
+            except Exception as exc:  # (ValueError: stencils that update a field in place cannot be re-run for timing)
+                s["tuned"] = {"skipped": f"{type(exc).__name__}: {exc}"[:120]}
         frozen.append((st.freeze(origin={p: origin3 for p in s["binding"]}, domain=(ni, nj, nk)), default_params(s["ir"], s["fixture"]), st))
     exchanger = None
     lib = runtime.load_library()
@@ -315,7 +334,7 @@ def main():
             "ms_per_step": round(ms, 5), "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": w["dtype"],
             "data": "synthetic",
             "config": {"workload": w["label"], "domain_per_gpu": [ni, nj, nk], "halo": list(w["halo"]),
-                       "stencils": [s["fixture"] for s in steps], "codegen_options": opts,
+                       "stencils": [s["fixture"] for s in steps], "codegen_options": opts, "tuned": [s.get("tuned") for s in steps] if args.tune else None,
                        "exchange": None if world == 1 or not w["exchanges"] else ("peer-memory pushes (b200_halo_push, symmetric memory) consumed by halo_wait kernels" if peer is not None else "NCCL SendRecv (b200_halo_exchange), serial"),
                        "kernels": [st.compiled.kernel_names() for _, _, st in frozen],
                        "l2": "two rotating buffer sets, each larger than the 126 MB L2"},
