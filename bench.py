@@ -448,7 +448,15 @@ def run_b200(args):
     peer_frozen = None
     if peer is not None:
         try:
-            hw_opts = {k: v for k, v in stencil.backend_options.items() if not k.startswith("tma")}
+            hw_opts = dict(stencil.backend_options)
+            if hw_opts.get("tma"):
+                # TMA variants are not combined with halo_wait: the fastest REGISTER-WINDOW candidate of the sweep instead
+                # (not the TMA winner minus its ring: its short J tiles are tuned for the ring — 0.183 vs 0.168 ms, r02q)
+                ldg = [c for c, _ms in (tuned if isinstance(tuned, list) else []) if not c.get("tma")]
+                base = {k: v for k, v in stencil.backend_options.items() if k in ("strategy", "device_sync")}
+                hw_opts = {**base, **(ldg[0] if ldg else {"interior_loop": True, "static_pitch": int(hw_opts.get("static_pitch", 0) or 0)})}
+                if not hw_opts.get("static_pitch"):
+                    hw_opts.pop("static_pitch", None)
             hw = B200Stencil(st_ir, {**hw_opts, "halo_wait": True, "device_sync": False})
             if all(k["kind"] == "stream" for k in hw.compiled.plan["kernels"]):
                 peer_frozen = hw.freeze(origin=origins, domain=domain)

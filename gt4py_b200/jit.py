@@ -103,7 +103,14 @@ def compile_cubin(source: str, options: Optional[Dict] = None, *, name: str = "s
     if cubin.exists() and cubin.stat().st_size > 0:
         return cubin.read_bytes()
     cu = cdir / f"{name}_{key}.cu"
-    cu.write_text(source, encoding="utf-8")
+    # several processes may compile the same variant at the same time (one rank per GPU, first call of a new variant):
+    # the source is published with an atomic rename (same content from every process, so the file nvcc reads is always
+    # complete) and every process compiles into its own output — a shared .cu that one rank is still writing would be
+    # an empty translation unit for another rank's nvcc, and the kernel-less cubin of that run would land in the cache
+    # ("named symbol not found", 8-GPU session r02q)
+    with tempfile.NamedTemporaryFile(dir=cdir, suffix=".cu.tmp", delete=False, mode="w", encoding="utf-8") as src_tmp:
+        src_tmp.write(source)
+    os.replace(src_tmp.name, cu)
     with tempfile.NamedTemporaryFile(dir=cdir, suffix=".cubin", delete=False) as tmp:
         tmp_path = tmp.name
     cmd = [nvcc_path(), *flags, "-cubin", "-I", str(CSRC), str(cu), "-o", tmp_path]

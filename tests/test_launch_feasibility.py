@@ -3,9 +3,12 @@ the cubin's resource usage (cuobjdump) against the sm_100a per-CTA limits.  A ke
 cannot be launched ("too many resources requested for launch", oversized parameter block) would
 otherwise only show up on the device."""
 
+import os
+import pathlib
 import re
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -97,3 +100,27 @@ def test_occupancy_cap_option_is_validated_and_reaches_the_plan():
     _check(st, {"fuse_columns": True, "seq_prefetch": 4, "seq_smem_pad": 110 * 1024}, "tridiagonal_f64_default")
     with pytest.raises(ValueError, match="seq_smem_pad"):
         codegen.generate(st, {"seq_smem_pad": 300 * 1024})
+
+
+def test_concurrent_compilation_of_one_variant_never_publishes_a_partial_cubin(tmp_path, monkeypatch):
+    """one rank per GPU: the first call of a new variant compiles it in every process at the same time"""
+    import concurrent.futures as cf
+    import subprocess as sp
+
+    monkeypatch.setenv("GT4PY_B200_CACHE", str(tmp_path))
+    src, _plan = codegen.generate(testing.load_ir("copy_f64", "default"), {"strategy": "auto"})
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from gt4py_b200 import jit\n"
+        "b = jit.compile_cubin(open(%r).read(), {'strategy': 'auto'}, name='race')\n"
+        "print(len(b))\n"
+    ) % (str(pathlib.Path(__file__).resolve().parent.parent), str(tmp_path / "src.cu"))
+    (tmp_path / "src.cu").write_text(src)
+    with cf.ThreadPoolExecutor(6) as ex:
+        outs = list(ex.map(lambda _n: sp.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GT4PY_B200_CACHE=str(tmp_path))), range(6)))
+    sizes = {o.stdout.strip() for o in outs}
+    assert all(o.returncode == 0 for o in outs), outs[0].stderr[-800:]
+    assert len(sizes) == 1 and int(sizes.pop()) > 1000
+    cubin = next(tmp_path.glob("race_*.cubin"))
+    elf = sp.run(["cuobjdump", "-elf", str(cubin)], capture_output=True, text=True).stdout
+    assert "b200_copy_f64" in elf
