@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--overlap", action="store_true", help="N>1: always overlap the halo exchange with the interior tiles")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: always exchange first, then compute the whole slab")
     ap.add_argument("--no-peer", action="store_true", help="N>1: do not use the peer-memory (symmetric memory) halo exchange")
-    ap.add_argument("--step-mode", default=None, choices=["serial", "overlap", "thin", "peer"],
+    ap.add_argument("--step-mode", default=None, choices=["serial", "overlap", "thin", "peer", "peer_tma"],
                     help="N>1: force one step schedule (default: a short trial of all of them, fastest on the max over ranks wins)")
     ap.add_argument("--watchdog", type=float, default=600.0, help="abort instead of hanging after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -445,7 +445,7 @@ def run_b200(args):
 
     # "peer" schedule: ONE launch of the `halo_wait` variant of the tuned kernel per step (boundary tiles last, waiting on
     # the neighbours' flags on the device) + one push kernel on the comm stream; no NCCL call, no boundary strips
-    peer_frozen = None
+    peer_frozen, peer_tma_frozen = None, None
     if peer is not None:
         try:
             hw_opts = dict(stencil.backend_options)
@@ -462,10 +462,21 @@ def run_b200(args):
                 peer_frozen = hw.freeze(origin=origins, domain=domain)
         except Exception as exc:
             peer_note = f"halo_wait kernel unavailable ({type(exc).__name__}: {str(exc)[:160]})"
-        okp = torch.tensor([1.0 if peer_frozen is not None else 0.0], device="cuda", dtype=torch.float64)
+        # "peer_tma": the same schedule with the TMA winner itself as the waiting kernel (flag acquire in the generic proxy,
+        # fence.proxy.async.global, then the bulk copies of the halo rows through the async proxy)
+        if stencil.backend_options.get("tma"):
+            try:
+                hwt = B200Stencil(st_ir, {**stencil.backend_options, "halo_wait": True, "device_sync": False})
+                if all(k["kind"] == "stream" for k in hwt.compiled.plan["kernels"]):
+                    peer_tma_frozen = hwt.freeze(origin=origins, domain=domain)
+            except Exception as exc:
+                peer_note = f"halo_wait TMA kernel unavailable ({type(exc).__name__}: {str(exc)[:160]})"
+        okp = torch.tensor([1.0 if peer_frozen is not None else 0.0, 1.0 if peer_tma_frozen is not None else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(okp, op=dist.ReduceOp.MIN)
-        if float(okp.item()) < 0.5:
+        if float(okp[0].item()) < 0.5:
             peer_frozen = None
+        if float(okp[1].item()) < 0.5:
+            peer_tma_frozen = None
 
     launches = 0
     mode = {"now": "serial"}
@@ -482,13 +493,13 @@ def run_b200(args):
         bufs = sets[i & 1]
         if exchanger is None:
             return frozen(**bufs)
-        if mode["now"] == "peer":
+        if mode["now"] in ("peer", "peer_tma"):
             # push my boundary rows into the neighbours' halo (comm stream, behind everything enqueued so far on the compute
             # stream); the whole slab in one launch whose boundary tiles wait for the neighbours' flags on the device
             runtime.check(lib.b200_event_record(ev_ready, main_stream))
             runtime.check(lib.b200_stream_wait_event(peer.stream, ev_ready))
             n = peer.push([(bufs["in_field"], HALO, HALO)])
-            return n + peer_frozen(**bufs, halo_wait=peer.wait_args())
+            return n + (peer_frozen if mode["now"] == "peer" else peer_tma_frozen)(**bufs, halo_wait=peer.wait_args())
         n = start_exchange(bufs)
         if mode["now"] == "serial":  # exchange, then the whole slab
             runtime.check(lib.b200_stream_wait_event(main_stream, ev_halo))
@@ -519,7 +530,7 @@ def run_b200(args):
     if exchanger is not None and args.step_mode != "auto":
         # a forced schedule is also the one that is warmed up (first-call work — module load, lazy specialisation —
         # must not land in the timed region)
-        avail_modes = ["serial", "overlap"] + (["thin"] if thin_frozen is not None else []) + (["peer"] if peer_frozen is not None else [])
+        avail_modes = ["serial", "overlap"] + (["thin"] if thin_frozen is not None else []) + (["peer"] if peer_frozen is not None else []) + (["peer_tma"] if peer_tma_frozen is not None else [])
         if args.step_mode not in avail_modes:
             raise SystemExit(f"bench.py: step mode {args.step_mode} is not available for this kernel ({peer_note})")
         mode["now"] = args.step_mode
@@ -528,7 +539,7 @@ def run_b200(args):
     barrier()
     overlap_trial = None
     if exchanger is not None:
-        modes = ["serial", "overlap"] + (["thin"] if thin_frozen is not None else []) + (["peer"] if peer_frozen is not None else [])
+        modes = ["serial", "overlap"] + (["thin"] if thin_frozen is not None else []) + (["peer"] if peer_frozen is not None else []) + (["peer_tma"] if peer_tma_frozen is not None else [])
         if args.step_mode != "auto":
             if args.step_mode not in modes:
                 raise SystemExit(f"bench.py: step mode {args.step_mode} is not available for this kernel")
@@ -774,7 +785,9 @@ def run_b200(args):
                 + {"serial": "(exchange, then the whole slab)", "overlap": "overlapped with the interior tiles, whole-tile boundary strips behind",
                    "thin": f"overlapped with the interior, {THIN}-row boundary strips on a high-priority side stream",
                    "peer": "replaced by peer-memory pushes over NVLink (b200_halo_push into symmetric memory) consumed inside ONE stencil launch "
-                           "per step (halo_wait kernel: boundary tiles last, device-side flag wait)"}[mode["now"]],
+                           "per step (halo_wait kernel: boundary tiles last, device-side flag wait)",
+                   "peer_tma": "replaced by peer-memory pushes over NVLink (b200_halo_push into symmetric memory) consumed inside ONE stencil launch "
+                               "per step (halo_wait variant of the bulk-async kernel: boundary tiles last, device-side flag wait + cross-proxy fence)"}[mode["now"]],
                 "schedule_trial": overlap_trial,
                 "multi_gpu_check": verify_note,
                 "exposed_comm_us_per_step": round((ms_per_step - kernel_ms) * 1e3, 1) if n_gpus > 1 else None,

@@ -498,6 +498,10 @@ class StreamKernel:
             w(f"        if (need_hi) b200::wait_flag({A}.g.halo_flag_hi, {A}.g.halo_epoch);")
             w("      }")
             w("      __syncwarp();")
+            if self.opts.get("tma"):
+                # the neighbour's rows were written through the generic proxy (NVLink stores) and acquired above by lane 0; the
+                # bulk copies of this warp read them through the ASYNC proxy: order the two proxies before the first copy
+                w("      b200::fence_proxy_async_global();")
             w("    }")
             w("  }")
         # window registers start at ONE, not zero: rows and lanes outside the tile are never loaded, whatever is computed

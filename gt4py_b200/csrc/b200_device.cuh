@@ -86,6 +86,8 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy writes to global memory (made visible to this thread by an acquire) -> later async-proxy reads (bulk copies)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -134,6 +136,7 @@ __device__ __forceinline__ bool elect_one() { return emu::lane() == 0; }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int) { *bar = 0; }
 __device__ __forceinline__ void mbar_fence_init() {}
 __device__ __forceinline__ void fence_async_smem() {}
+__device__ __forceinline__ void fence_proxy_async_global() {}
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   if ((*bar >> 32) != 0) emu::fail("mbarrier: expect_tx on a barrier with a phase still in flight");
   *bar += (unsigned long long)bytes << 32;

@@ -68,8 +68,10 @@ class Gen:
             return f"{self.r.choice(['min', 'max'])}({a}, {b})"
         if c < 0.72:
             return f"abs({a})"
-        if c < 0.80:
+        if c < 0.78:
             return f"({a} / (abs({b}) + 1.0))"
+        if c < 0.84:  # launch-invariant divisor: the hoisted-reciprocal division of the generators (b200::DivInv)
+            return f"({a} / {self.r.choice(['3.0', '0.75', '60.0', '7.0', '1.0e-3', '(2.0 * 3.0)'])})"
         cond = f"({self.leaf(inputs, temps, **kw)} {self.r.choice(['>', '<', '>=', '<='])} {self.leaf(inputs, temps, **kw)})"
         return f"({a} if {cond} else {b})"
 
@@ -188,8 +190,12 @@ def run_case(source: str, fname: str, dtype: str, seed: int, workdir: pathlib.Pa
         ref = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
         numpy_oracle.run(st, ref, params, domain, origins)
         pitch = {-(-v.shape[0] // 32) * 32 for v in fields.values() if v is not None}
+        sp = pitch.pop() if len(pitch) == 1 else 0
         variants = [{}, {"strategy": "point"}, {"fuse_loops": False, "seq_prefetch": 2}, {"seq_cache": False},
-                    {"interior_loop": True, "static_pitch": pitch.pop() if len(pitch) == 1 else 0, "tile_j": 32}]  # fmt: skip
+                    {"interior_loop": True, "static_pitch": sp, "tile_j": 32},
+                    {"k_order": True, "period": 4, "div_slow": "inline", "col_smem": True, "seq_prefetch": 4},
+                    {"k_order": False, "interior_loop": True, "static_pitch": sp, "tma": 2, "tile_j": 16, "seq_rotate": True, "seq_prefetch": 2, "fuse_columns": True},
+                    {"div_inv": False, "seq_rotate": False, "col_hints": True}]  # fmt: skip
         for opts in variants:
             es = EmuStencil(st, opts, name=f"{fname}.{variant}")
             for layout in (None, "b200"):
