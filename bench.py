@@ -191,6 +191,9 @@ def cpu_arm(steps: int, warmup: int, max_seconds: float):
         "sample": (f"{'reference gt4py numpy backend (baseline/_ref), StencilObject.__call__' if k == 'reference' else 'oracle port (' + kind + ')'}"
                    f" on the whole {NI}x{NJ}x{NK} fp32 domain per step, cut into {cores} K slabs of {NK // cores}-{-(-NK // cores)} levels, one "
                    f"process per usable core started together ({os.cpu_count()} host cores present), {steps} timed steps"),
+        # north_star: "... and gt:cpu_kfirst where it builds offline" — it does not: its generated C++ needs the GridTools
+        # headers of the gridtools_cpp package, which is not in this image
+        "gt_cpu_kfirst": "not available: the reference's gt:cpu_kfirst backend needs the gridtools_cpp C++ headers, absent offline",
     }  # fmt: skip
     return line, ms_step, steps
 
