@@ -225,6 +225,19 @@ def _host_view(arg):
     return arr, runtime.ArrayView(arr.ctypes.data, arr.shape, tuple(s // arr.itemsize for s in arr.strides), arr.dtype, arg)
 
 
+def default_host_chunks(options, nk: int) -> int:
+    """K slabs of a host-array call: option `host_chunks`, else GT4PY_B200_HOST_CHUNKS, else HOST_CHUNKS.  The call returns
+    when the result is in host memory, so every call pays the pipeline's fill (H2D of the first slab) and drain (D2H of the
+    last one): thinner slabs shorten both, while the per-slab launches stay hidden behind the PCIe transfers."""
+    import os
+
+    n = options.get("host_chunks") or os.environ.get("GT4PY_B200_HOST_CHUNKS") or HOST_CHUNKS
+    return max(1, min(int(n), int(nk)))
+
+
+HOST_CHUNKS = 10
+
+
 def host_call(stencil, field_args, parameter_args, domain, origin, *, validate_args=True, exec_info=None) -> None:
     """One stencil application on arguments that live in HOST memory — an extension over the reference, whose GPU
     backends refuse CPU arrays (storage/cartesian/utils.py:176-215): code written for `backend="numpy"` with plain
@@ -282,7 +295,7 @@ def host_call(stencil, field_args, parameter_args, domain, origin, *, validate_a
         if pipe is None:
             try:
                 pipe = HostPipeline(stencil, {n: dev_args[n] for n in used}, origin=origin, domain=domain,
-                                    n_chunks=int(stencil.backend_options.get("host_chunks", 10)))  # fmt: skip
+                                    n_chunks=default_host_chunks(stencil.backend_options, domain[2]))  # fmt: skip
             except ValueError:
                 pipe = False  # e.g. a field that is not 3-D: serial path
             cache[pkey] = pipe
