@@ -446,6 +446,39 @@ def run_b200(args):
         if float(avail.item()) < 0.5:
             thin_frozen = None
 
+    hw_pick, hwt_pick = None, None
+
+    def halo_wait_variant(base_opts):
+        """The `halo_wait` form of a kernel variant, at the register cap that runs fastest: the flag-wait code costs 8-14
+        registers (LDG 44 -> 54, TMA 50 -> 64: two resident CTAs per SM less, 0.169 -> 0.194 ms for the bare LDG kernel,
+        r02u) which `__launch_bounds__` gives back without spills.  Timed without flags (epoch 0: nobody waits)."""
+        best = (None, None, float("inf"))
+        for mb in (None, 10, 11, 12):
+            opts = {**base_opts, "halo_wait": True, "device_sync": False, **({"min_blocks": mb} if mb else {})}
+            try:
+                cand = B200Stencil(st_ir, opts)
+                if not all(k["kind"] == "stream" for k in cand.compiled.plan["kernels"]):
+                    continue
+                fr = cand.freeze(origin=origins, domain=domain)
+                for i in range(3):
+                    fr(**sets[i & 1])
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for i in range(20):
+                    fr(**sets[i & 1])
+                b.record()
+                b.synchronize()
+                ms = a.elapsed_time(b) / 20
+            except Exception:
+                if mb is None:
+                    raise
+                continue
+            if ms < best[2]:
+                best = (fr, mb, ms)
+        if best[0] is None:
+            raise RuntimeError("no streaming halo_wait kernel")
+        return best[0], {"min_blocks": best[1], "bare_kernel_ms": round(best[2], 5)}
+
     # "peer" schedule: ONE launch of the `halo_wait` variant of the tuned kernel per step (boundary tiles last, waiting on
     # the neighbours' flags on the device) + one push kernel on the comm stream; no NCCL call, no boundary strips
     peer_frozen, peer_tma_frozen = None, None
@@ -460,18 +493,14 @@ def run_b200(args):
                 hw_opts = {**base, **(ldg[0] if ldg else {"interior_loop": True, "static_pitch": int(hw_opts.get("static_pitch", 0) or 0)})}
                 if not hw_opts.get("static_pitch"):
                     hw_opts.pop("static_pitch", None)
-            hw = B200Stencil(st_ir, {**hw_opts, "halo_wait": True, "device_sync": False})
-            if all(k["kind"] == "stream" for k in hw.compiled.plan["kernels"]):
-                peer_frozen = hw.freeze(origin=origins, domain=domain)
+            peer_frozen, hw_pick = halo_wait_variant(hw_opts)
         except Exception as exc:
             peer_note = f"halo_wait kernel unavailable ({type(exc).__name__}: {str(exc)[:160]})"
         # "peer_tma": the same schedule with the TMA winner itself as the waiting kernel (flag acquire in the generic proxy,
         # fence.proxy.async.global, then the bulk copies of the halo rows through the async proxy)
         if stencil.backend_options.get("tma"):
             try:
-                hwt = B200Stencil(st_ir, {**stencil.backend_options, "halo_wait": True, "device_sync": False})
-                if all(k["kind"] == "stream" for k in hwt.compiled.plan["kernels"]):
-                    peer_tma_frozen = hwt.freeze(origin=origins, domain=domain)
+                peer_tma_frozen, hwt_pick = halo_wait_variant(stencil.backend_options)
             except Exception as exc:
                 peer_note = f"halo_wait TMA kernel unavailable ({type(exc).__name__}: {str(exc)[:160]})"
         okp = torch.tensor([1.0 if peer_frozen is not None else 0.0, 1.0 if peer_tma_frozen is not None else 0.0], device="cuda", dtype=torch.float64)
@@ -792,6 +821,7 @@ def run_b200(args):
                    "peer_tma": "replaced by peer-memory pushes over NVLink (b200_halo_push into symmetric memory) consumed inside ONE stencil launch "
                                "per step (halo_wait variant of the bulk-async kernel: boundary tiles last, device-side flag wait + cross-proxy fence)"}[mode["now"]],
                 "schedule_trial": overlap_trial,
+                "halo_wait_kernels": {"peer": hw_pick, "peer_tma": hwt_pick} if n_gpus > 1 else None,
                 "multi_gpu_check": verify_note,
                 "exposed_comm_us_per_step": round((ms_per_step - kernel_ms) * 1e3, 1) if n_gpus > 1 else None,
                 "l2": "inputs larger than L2: 2 rotating buffer sets x 1.0 GB working set vs 126 MB L2",

@@ -443,6 +443,7 @@ class StreamKernel:
         w(f"  const int nk = {A}.g.k_hi - {A}.g.k_lo;")
         w("  if (task >= (long long)nseg * ntj * nk) return;")
         halo_wait = bool(self.opts.get("halo_wait", False))
+
         # task order.  Default: segment fastest, level slowest (plane by plane).  A kernel that reads a field at K offsets
         # (pp[0,0,+-1] of the pressure gradient) touches every plane of that field from three levels: with the LEVEL
         # fastest, the warps of a CTA and of its neighbours work on consecutive levels of the same rows at the same time,
