@@ -452,7 +452,10 @@ class StreamKernel:
         kfast = self.opts.get("k_order", "auto")
         kfast = any(v.kind == "in" and v.dk != 0 for v in self.values) if kfast == "auto" else bool(kfast)
         self.kfast = kfast
-        if halo_wait and kfast:
+        # (development switches of the halo_wait form: task order and wait block separately)
+        halo_order = halo_wait and bool(self.opts.get("halo_order", True))
+        halo_block = halo_wait and bool(self.opts.get("halo_block", True))
+        if halo_order and kfast:
             w("  int seg, tj, kk;")
             w("  if (ntj >= 3) {")
             w("    const long long n_int = (long long)nseg * (ntj - 2) * nk;   // interior tiles first")
@@ -464,7 +467,7 @@ class StreamKernel:
             w(f"  const int k = {A}.g.k_lo + (int)(task % nk);")
             w("  const int seg = (int)((task / nk) % nseg);")
             w("  const int tj = (int)(task / ((long long)nk * nseg));")
-        elif halo_wait:
+        elif halo_order:
             # multi-GPU J slabs with the peer-memory halo exchange: the first and the last J tile read rows the neighbours
             # push into this rank's halo while this kernel is already running -> those tiles come LAST in the task order
             # (all levels), behind every interior tile, so that by the time they start their halo has normally arrived
@@ -487,7 +490,7 @@ class StreamKernel:
         w("  const bool own = (lane >= HL) && (lane < HL + SQ);")
         w("  const int T_lo = Y0 + tj * TJ;")
         w("  const int T_hi = (T_lo + TJ < Y1) ? T_lo + TJ : Y1;")
-        if halo_wait:
+        if halo_block:
             ins_nj = [v.nj for v in self.values if v.kind == "in"]
             lo_rows, hi_rows = min([0] + [n[0] for n in ins_nj]), max([0] + [n[1] for n in ins_nj])
             w(f"  if ({A}.g.halo_epoch) {{   // tiles that read halo rows wait until the neighbour's rows of this step have landed")
