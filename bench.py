@@ -450,10 +450,13 @@ def run_b200(args):
 
     def halo_wait_variant(base_opts):
         """The `halo_wait` form of a kernel variant, at the register cap that runs fastest: the flag-wait code costs 8-14
-        registers (LDG 44 -> 54, TMA 50 -> 64: two resident CTAs per SM less, 0.169 -> 0.194 ms for the bare LDG kernel,
-        r02u) which `__launch_bounds__` gives back without spills.  Timed without flags (epoch 0: nobody waits)."""
+        registers (LDG 44 -> 54, TMA 50 -> 64: two resident CTAs per SM less, 0.169 -> 0.193 ms for the bare LDG kernel,
+        r02u) which `__launch_bounds__` gives back without spills (0.182 ms at a 44-register cap, r02y).  Timed without
+        flags (epoch 0: nobody waits)."""
         best = (None, None, float("inf"))
-        for mb in (None, 10, 11, 12):
+        threads = 32 * int(base_opts.get("warps", 4))
+        caps = sorted({min(32, 2048 // threads, 65536 // (regs * threads)) for regs in (48, 44, 40)})  # resident CTAs per SM at that many registers
+        for mb in (None, *caps):
             opts = {**base_opts, "halo_wait": True, "device_sync": False, **({"min_blocks": mb} if mb else {})}
             try:
                 cand = B200Stencil(st_ir, opts)
