@@ -954,8 +954,11 @@ class StreamKernel:
                 # statement's whole group — all V elements — shares one range check (flush_pre)
                 nm = f"dq{len(divq)}"
                 acc = f"dbad{divg[0]}{'f' if ct == 'float' else 'd'}"
-                divq.append((nm, dv, ct, acc))
-                self.pre.append(f"const {ct} {nm}_a = {a}; {ct} {nm} = b200::div_inv_try({nm}_a, {dv}, {acc});")
+                # a dividend that contains an earlier quotient of the group (x / dx / dy) must be re-evaluated from the
+                # redone quotient when the group falls back to IEEE divisions
+                redo = a if any(q[0] in a for q in divq[divg[1]:]) else None
+                divq.append((nm, dv, ct, acc, redo))
+                self.pre.append(f"{ct} {nm}_a = {a}; {ct} {nm} = b200::div_inv_try({nm}_a, {dv}, {acc});")
                 return nm
 
             def expr(self, n):
@@ -970,7 +973,7 @@ class StreamKernel:
             ct = CT[d["dtype"]]
             L.append(ind2 + f"{ct} " + ", ".join(f"l_{d['name']}_{e} = ({ct})0" for e in range(V)) + ";")
 
-        divq: List[Tuple[str, str, str, str]] = []  # quotients of the stage so far: (name, DivInv, C type, accumulator)
+        divq: List[tuple] = []  # quotients of the stage so far: (name, DivInv, C type, accumulator, dividend to re-evaluate or None)
         divg = [0, 0]  # [current group index, first quotient of the current group]
 
         def flush_pre():
@@ -987,7 +990,9 @@ class StreamKernel:
                 cond = " || ".join(f"b200::div_inv_bad({acc})" for acc in sorted({q[3] for q in group}))
                 L.append(ind2 + f"if (__builtin_expect(__any_sync(0xffffffffu, {cond}), 0)) {{")
                 L.append(ind2 + "  B200_TRACE(6);")
-                for nm, dv, ct, acc in group:
+                for nm, dv, ct, acc, redo in group:
+                    if redo is not None:
+                        L.append(ind2 + f"  {nm}_a = {redo};")
                     # (out-of-line: a call per quotient keeps the loop small but its ABI costs registers once the loop is
                     #  unrolled 4+ times — 71 / 96 / 108 for upwind5 at period 2 / 4 / 8 — hence inline there)
                     inline = kern.opts.get("div_slow", "call" if kern.U <= 2 else "inline") == "inline"

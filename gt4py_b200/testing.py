@@ -39,6 +39,8 @@ CASE_SPECS: Dict[str, Dict[str, Any]] = {
     "ints_bools": {"inputs": "ints"},
     "casts": {"inputs": "ints"},
     "sections_koff_f64": {"domain": (70, 40, 6)},
+    "div_param_f32": {"inputs": "div_specials", "domain": (70, 23, 3), "params": {"dx": np.float32(0.1), "dy": np.float32(-2.5e-3)}},
+    "div_param_col_f64": {"inputs": "div_specials", "domain": (37, 9, 7), "params": {"dz": np.float64(0.3)}},
 }
 
 
@@ -111,6 +113,20 @@ def make_case_data(stencil, name: Optional[str] = None, domain=None, seed: int =
         fields["idx"] = rng.integers(-2, 3, size=shapes["idx"]).astype(np.int32)
     elif recipe == "varoff_up":
         fields["idx"] = rng.integers(0, 3, size=shapes["idx"]).astype(np.int32)
+    elif recipe == "div_specials":
+        # operands that leave the guarded exponent range of the hoisted-reciprocal division (csrc/b200_device.cuh, DivInv)
+        for n, arr in fields.items():
+            if arr is None or arr.dtype.kind != "f" or n.startswith("out"):
+                continue
+            tiny, huge = (1e-44, 1e30) if arr.dtype == np.float32 else (5e-324, 1e300)
+            flat = arr.reshape(-1)
+            idx = rng.permutation(flat.size)
+            m = max(1, flat.size // 16)
+            for j, val in enumerate((0.0, -0.0, np.inf, -np.inf, np.nan, tiny, -tiny)):
+                flat[idx[j * m:(j + 1) * m]] = val
+            flat[idx[7 * m:8 * m]] *= arr.dtype.type(huge)
+            flat[idx[8 * m:9 * m]] *= arr.dtype.type(1e-30 if arr.dtype == np.float32 else 1e-290)
+            flat[idx[9 * m:10 * m]] -= arr.dtype.type(0.5)
     elif recipe == "fastwaves":
         if "hhl" in fields and fields["hhl"] is not None:
             nk = fields["hhl"].shape[2]

@@ -335,6 +335,24 @@ def scale_param_f32(a: F32, b: F32, *, alpha: np.float32, n: np.int32):
         b = alpha * a + n
 
 
+@case("div_param_f32", build={"literal_float_precision": 32})
+def div_param_f32(a: F32, b: F32, out: F32, out2: F32, *, dx: np.float32, dy: np.float32):
+    """Divisions by launch invariants (scalar parameters, literals): the b200 generators divide through a hoisted
+    reciprocal; the inputs of this case hold zeros of both signs, infinities, NaNs, subnormals and huge values."""
+    with computation(PARALLEL), interval(...):
+        out = a[1, 0, 0] / (60.0 * dx) - b[0, -1, 0] / dy + a[0, 0, 0] / 3.0
+        out2 = (a[0, 0, 0] - b[0, 0, 0]) / (dx * dy) / 7.0
+
+
+@case("div_param_col_f64")
+def div_param_col_f64(a: F64, out: F64, *, dz: np.float64):
+    with computation(FORWARD):
+        with interval(0, 1):
+            out = a / dz
+        with interval(1, None):
+            out = out[0, 0, -1] / 3.0 + a / (2.0 * dz)
+
+
 @case("k_intervals_f64")
 def k_intervals_f64(a: F64, b: F64):
     with computation(PARALLEL):
