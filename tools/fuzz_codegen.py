@@ -187,6 +187,16 @@ def run_case(source: str, fname: str, dtype: str, seed: int, workdir: pathlib.Pa
     for variant, st in irs.items():
         domain = (rng.choice([5, 33, 67, 130]), rng.choice([3, 9, 70]), max(rng.choice([2, 3, 5]), int(st["domain_info"]["min_k"])))
         fields, params, origins, domain = testing.make_case_data(st, fname, domain=domain, seed=seed)
+        if seed % 2:  # special values: the guarded fast paths of the generators (hoisted-reciprocal division) must fall back
+            srng = np.random.default_rng(seed)
+            for arr in fields.values():
+                if arr is not None and arr.dtype.kind == "f":
+                    flat = arr.reshape(-1)
+                    idx = srng.permutation(flat.size)
+                    m = max(1, flat.size // 12)
+                    for j, val in enumerate((0.0, -0.0, np.inf, -np.inf, np.nan, 1e-44 if arr.dtype == np.float32 else 5e-324)):
+                        flat[idx[j * m:(j + 1) * m]] = val
+                    flat[idx[6 * m:7 * m]] *= arr.dtype.type(1e30)
         ref = {k: (v.copy() if v is not None else None) for k, v in fields.items()}
         numpy_oracle.run(st, ref, params, domain, origins)
         pitch = {-(-v.shape[0] // 32) * 32 for v in fields.values() if v is not None}
