@@ -134,7 +134,10 @@ def test_workload_bench_dry_run(monkeypatch, capsys, workload):
     assert "SMOKE RUN" in line["config"]["workload"] and line["cpu_baseline"]["kind"] == "port"
 
 
-@pytest.mark.parametrize("extra", [[], ["--step-mode", "thin"], ["--no-overlap"]])
+TMA_WINNER = ["--options", '{"interior_loop": true, "static_pitch": 96, "tma": 2, "tile_j": 16, "prefetch": 1, "tma_mode": "bulk"}']
+
+
+@pytest.mark.parametrize("extra", [[], ["--step-mode", "thin"], ["--no-overlap"], TMA_WINNER])
 def test_bench_main_dry_run_two_ranks(monkeypatch, capsys, extra):
     """the N>1 control flow of bench.py (schedule self-check, trial, matched step counts) with the device,
     torch.distributed and the halo exchanger stubbed: rank 0 of a 2-rank job"""
@@ -231,6 +234,14 @@ def test_bench_main_dry_run_two_ranks(monkeypatch, capsys, extra):
     assert line["n_gpus"] == 2 and "cpu_baseline" not in line and calls["exchange"] > 6
     par = line["config"]["parallelism"]
     thin_strips = [c for c in calls["subboxes"] if c[0] in ((0, 64, 0, 16), (0, 64, 144, 160))]
+    if extra == TMA_WINNER:
+        # a bulk-async winner: the peer schedule exists twice — with the winner's own halo_wait form (cross-proxy fence) and
+        # with a register-window kernel; both were built at the register cap bench.py timed fastest
+        trial = line["config"]["schedule_trial"]["ms_per_step"]
+        assert set(trial) >= {"serial", "overlap", "thin", "peer", "peer_tma"}
+        picks = line["config"]["halo_wait_kernels"]
+        assert set(picks) == {"peer", "peer_tma"} and all("bare_kernel_ms" in p for p in picks.values())
+        return
     if extra == ["--no-overlap"]:
         assert "then the whole slab" in par and not thin_strips and line["gpu_launches"] == 3 * (3 + 1)
     elif extra:
