@@ -41,16 +41,16 @@ step 300  ncu_hdiff  ncu --set full --clock-control none --import-source on -k r
                      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-pipeline --options "$WIN"
 # the other BASELINE configs (single GPU) with the variants the sweeps found (profiles/README.md)
 step 300  cfg3       python tools/bench_workloads.py --workload tridiagonal --steps 20
-step 300  cfg4       python tools/bench_workloads.py --workload upwind5 --steps 20 --options '{"l2_prefetch": 1}'
-step 300  cfg5       python tools/bench_workloads.py --workload fastwaves --steps 10 --options '{"tma": 3, "tile_j": 32, "prefetch": 0}'
+step 300  cfg4       python tools/bench_workloads.py --workload upwind5 --steps 20 --tune
+step 400  cfg5       python tools/bench_workloads.py --workload fastwaves --steps 10 --tune
 step 300  x2         python tools/bench_workloads.py --workload hdiff_x2 --steps 20
 step 300  x2_fused   python tools/bench_workloads.py --workload hdiff_x2 --fuse --steps 20
 step 300  ncu_tri    ncu --set full --clock-control none --import-source on -k regex:tridiagonal -c 2 -f -o "$OUT/${TAG}_tridiagonal" \
                      python tools/bench_workloads.py --workload tridiagonal --steps 2 --warmup 3
 step 300  ncu_up5    ncu --set full --clock-control none --import-source on -k regex:upwind5 -s 4 -c 1 -f -o "$OUT/${TAG}_upwind5" \
-                     python tools/bench_workloads.py --workload upwind5 --steps 2 --warmup 3 --options '{"l2_prefetch": 1}'
+                     python tools/bench_workloads.py --workload upwind5 --steps 2 --warmup 3
 step 300  ncu_fw     ncu --set full --clock-control none --import-source on -k regex:b200_fw_ -s 12 -c 6 -f -o "$OUT/${TAG}_fastwaves" \
-                     python tools/bench_workloads.py --workload fastwaves --steps 2 --warmup 3 --options '{"tma": 3, "tile_j": 32, "prefetch": 0}'
+                     python tools/bench_workloads.py --workload fastwaves --steps 2 --warmup 3
 step 300  ncu_fused  ncu --set full --clock-control none --import-source on -k regex:fused2_stream0 -s 4 -c 1 -f -o "$OUT/${TAG}_hdiff_fused2" \
                      python tools/bench_workloads.py --workload hdiff_x2 --fuse --steps 3 --warmup 3
 grep -h '"metric"' "$OUT/${TAG}"_bench*.log "$OUT/${TAG}"_cfg*.log "$OUT/${TAG}"_x2*.log 2>/dev/null | cut -c1-700
