@@ -327,6 +327,22 @@ def main():
     bpc = sum(s["bytes_per_cell"] for s in steps)
     peak, peak_src = headline.measured_peaks()
     achieved = ni * nj * nk * bpc / kernel_ms / 1e6
+    # DRAM traffic per step from the committed ncu captures of these kernels (profiles/workload_traffic.json: per kernel, the
+    # variant that was captured is named there) — only for the domain the captures were taken on
+    traffic, traffic_src = None, None
+    tfile = ROOT / "profiles" / "workload_traffic.json"
+    if tfile.exists() and args.shrink == 1:
+        try:
+            table = json.loads(tfile.read_text())
+            names = [k for _, _, st in frozen for k in st.compiled.kernel_names()]
+            have = [k for k in names if k in table and list(table[k]["domain"]) == [ni, nj, nk]]
+            if have:
+                traffic = float(sum(table[k]["dram_bytes_per_launch"] for k in have))
+                missing = [k for k in names if k not in have]
+                traffic_src = ("profiles/workload_traffic.json: sum over " + ", ".join(f"{k} (captured variant {table[k]['captured_variant']})" for k in have)
+                               + (f"; no capture for {', '.join(missing)}" if missing else ""))
+        except Exception:
+            traffic, traffic_src = None, None
     if rank == 0:
         line = {
             "metric": f"Mcell-updates/s + achieved HBM GB/s, {args.workload}",
@@ -340,7 +356,7 @@ def main():
                        "l2": "two rotating buffer sets, each larger than the 126 MB L2"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": round(kernel_ms, 5),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": round(kernel_ms, 5),
                          "algorithmic_bytes_per_launch": ni * nj * nk * bpc, "bytes_per_cell": bpc},
             "clocks": clocks.summary() if clocks is not None else None,
         }  # fmt: skip
