@@ -31,3 +31,42 @@ def test_unverified_gpu_tests_pass_on_the_fake_device():
                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)  # fmt: skip
     assert proc.returncode == 0, proc.stdout[-3000:]
     assert " passed" in proc.stdout and "failed" not in proc.stdout
+
+
+def test_autotune_of_stencils_that_update_fields_in_place_on_the_fake_device():
+    """B200Stencil.autotune on column solvers (sup / rhs of the Thomas solver are READ_WRITE): every candidate starts from
+    a saved copy of the in-place fields, is validated after one application, and the caller's inputs are restored."""
+    import numpy as np
+    import torch
+
+    if _have_gpu() or os.environ.get("B200_EMULATE_DEVICE") == "1":
+        pytest.skip("real device present / already emulating")
+    from emu import fake_device as fd
+
+    mp = pytest.MonkeyPatch()
+    fd.install(mp)
+    try:
+        from gt4py_b200 import storage, testing
+        from gt4py_b200.stencil import B200Stencil
+        from oracle import numpy_oracle
+
+        for name in ("tridiagonal_f64", "fw_wsolve_f32"):
+            st = testing.load_ir(name, "default")
+            fields, params, origins, domain = testing.make_case_data(st, name, domain=(37, 5, 9), seed=3)
+            ref = {k: v.copy() for k, v in fields.items()}
+            numpy_oracle.run(st, ref, params, domain, origins)
+            dev = {k: storage.from_array(v, aligned_index=origins[k]) for k, v in fields.items()}
+            stencil = B200Stencil(st, {"device_sync": False})
+            cands = [{}, {"seq_rotate": False}, {"seq_prefetch": 2}, {"fuse_columns": True}, {"seq_cache": False}]
+            tuned = stencil.autotune(dev, params, domain=domain, origin=origins, candidates=cands, iters=2, refine=1)
+            assert len(tuned) >= 3 and stencil.tune_rejected == []
+            for n, v in fields.items():  # the in-place inputs are back
+                if st["field_info"][n]["access"] == "READ_WRITE":
+                    np.testing.assert_array_equal(dev[n].get(), v, err_msg=f"{name}:{n} not restored")
+            stencil(**dev, **params, origin=origins, domain=domain)
+            torch.cuda.synchronize()
+            for n in testing.written_fields(st):
+                box = tuple(slice(o, o + d) for o, d in zip(origins[n], domain))
+                np.testing.assert_array_equal(dev[n].get()[box], ref[n][box], err_msg=f"{name}:{n}")
+    finally:
+        mp.undo()

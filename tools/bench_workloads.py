@@ -159,6 +159,8 @@ TUNE_CANDIDATES = (
     {**P, "tma": 3, "tile_j": 32, "prefetch": 0}, {**P, "tma": 3, "tile_j": 32, "prefetch": 0, "tma_mode": "bulk"},
     {**P, "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk"}, {**P, "tma": 3, "tile_j": 16, "prefetch": 1, "tma_mode": "bulk"},
     {**P, "tma": 3, "tile_j": 32, "prefetch": 1, "tma_mode": "bulk", "stcs": True},
+    # column kernels (the streaming options above do not change their code: duplicates are skipped by the tuner)
+    {"seq_rotate": False}, {"seq_rotate": True}, {"seq_prefetch": 2}, {"seq_prefetch": 4}, {"fuse_columns": True},
 )  # fmt: skip
 
 
@@ -242,7 +244,7 @@ def main():
                 tuned = st.autotune({p: sets[0][b] for p, b in s["binding"].items()}, default_params(s["ir"], s["fixture"]), domain=(ni, nj, nk),
                                     origin={p: origin3 for p in s["binding"]}, candidates=TUNE_CANDIDATES, iters=10, refine=2)  # fmt: skip
                 s["tuned"] = {"options": tuned[0][0], "ms": tuned[0][1], "candidates": len(tuned)}
-            except Exception as exc:  # (ValueError: stencils that update a field in place cannot be re-run for timing)
+            except Exception as exc:  # the measurement must survive a tuner problem: default variant, reason recorded
                 s["tuned"] = {"skipped": f"{type(exc).__name__}: {exc}"[:120]}
         frozen.append((st.freeze(origin={p: origin3 for p in s["binding"]}, domain=(ni, nj, nk)), default_params(s["ir"], s["fixture"]), st))
     exchanger = None
