@@ -24,12 +24,19 @@ def test_workload_plans_match_the_baseline_configs():
     assert p["domain_per_gpu"] == (512, 512, 160) and p["bytes_per_cell"] == [56] and p["exchanges"] == {}
 
 
-def test_workload_cpu_baseline_runs_the_oracle_chain():
+def test_workload_cpu_baseline_runs_the_reference_numpy_backend_or_the_oracle_chain(monkeypatch):
     import bench_workloads as bw
 
     w = bw.workload("fastwaves", 1)
     r = bw.cpu_baseline(bw.step_description(w), w["halo"], sample=(12, 10, 6))
-    assert r["value"] > 0 and r["kind"] == "port" and r["cores"] == 1
+    # the reference's own numpy backend where the reference package is importable (baseline/_ref or /root/reference) ...
+    assert r["value"] > 0 and r["kind"] in ("reference", "port") and r["cores"] == 1
+    if r["kind"] == "reference":
+        assert "reference gt4py numpy backend" in r["sample"]
+    # ... else (simulated here) the oracle port
+    monkeypatch.setenv("B200_NO_REFERENCE", "1")
+    r = bw.cpu_baseline(bw.step_description(w), w["halo"], sample=(12, 10, 6))
+    assert r["value"] > 0 and r["kind"] == "port" and r["sample"].startswith("oracle")
 
 
 def test_reference_arm_prints_one_json_line():

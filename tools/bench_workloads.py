@@ -123,9 +123,34 @@ def default_params(st, fixture):
     return out
 
 
-def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
-    from oracle import numpy_oracle
+def _reference_runners(steps):
+    """The stencils of a step built by the REFERENCE numpy backend (gt4py from baseline/_ref, tools/refenv.py), or None
+    when the reference is not importable here / a step is not a fixture definition (fused IRs)."""
+    try:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import refenv
 
+        if not refenv.enable_gt4py():
+            return None
+        import warnings
+
+        warnings.filterwarnings("ignore")
+        import stencil_defs
+        from gt4py.cartesian import gtscript
+
+        runners = []
+        for s in steps:
+            case = stencil_defs.REGISTRY[s["fixture"]]
+            runners.append(gtscript.stencil(backend="numpy", definition=case["definition"], externals=case["externals"] or {},
+                                            name=f"{s['fixture']}_workload_ref", **case["build"]))  # fmt: skip
+        return runners
+    except Exception:
+        return None
+
+
+def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
+    """CPU arm of a workload on a bounded sub-domain: the reference's own numpy backend (`kind: "reference"`) where gt4py is
+    importable (baseline/_ref travels to the GPU box), else the oracle port."""
     rng = np.random.default_rng(0)
     shape = tuple(sample[a] + 2 * halo[a] for a in range(3))
     buffers = {}
@@ -134,13 +159,30 @@ def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
             if p["t"] == "field":
                 buffers.setdefault(s["binding"][p["name"]], p["dtype"])
     data = make_inputs(buffers, shape, rng)
+    refs = _reference_runners(steps)
+    if refs is not None:
+        kind = "reference"
 
-    def one():
-        for s in steps:
-            fields = {p: data[b] for p, b in s["binding"].items()}
-            numpy_oracle.run(s["ir"], fields, default_params(s["ir"], s["fixture"]), sample, {p: tuple(halo) for p in fields})
+        def one():
+            for s, ref in zip(steps, refs):
+                fields = {p: data[b] for p, b in s["binding"].items()}
+                ref(**fields, **default_params(s["ir"], s["fixture"]), origin={p: tuple(halo) for p in fields}, domain=tuple(sample))
 
-    one()
+    else:
+        kind = "port"
+        from oracle import numpy_oracle
+
+        def one():
+            for s in steps:
+                fields = {p: data[b] for p, b in s["binding"].items()}
+                numpy_oracle.run(s["ir"], fields, default_params(s["ir"], s["fixture"]), sample, {p: tuple(halo) for p in fields})
+
+    try:
+        one()
+    except Exception:
+        if kind != "reference":
+            raise
+        return cpu_baseline_port(steps, halo, sample, updates)
     times = []
     t_end = time.perf_counter() + 10.0
     while len(times) < 2 or (time.perf_counter() < t_end and len(times) < 30):
@@ -148,8 +190,22 @@ def cpu_baseline(steps, halo, sample=(128, 128, 16), updates=1):
         one()
         times.append(time.perf_counter() - t0)
     cells = sample[0] * sample[1] * sample[2] * updates
-    return {"value": round(cells / float(np.median(times)) / 1e6, 3), "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
-            "sample": f"oracle, {sample[0]}x{sample[1]}x{sample[2]} sub-domain, {len(times)} steps, median ({os.cpu_count()} host cores available, NumPy uses 1)"}  # fmt: skip
+    what = "reference gt4py numpy backend (baseline/_ref), StencilObject.__call__" if kind == "reference" else "oracle"
+    return {"value": round(cells / float(np.median(times)) / 1e6, 3), "unit": "Mcell-updates/s", "cores": 1, "kind": kind,
+            "sample": f"{what}, {sample[0]}x{sample[1]}x{sample[2]} sub-domain, {len(times)} steps, median ({os.cpu_count()} host cores available, NumPy uses 1)"}  # fmt: skip
+
+
+def cpu_baseline_port(steps, halo, sample=(128, 128, 16), updates=1):
+    """the oracle port, used when the reference is not importable or refuses the call"""
+    prev = os.environ.get("B200_NO_REFERENCE")
+    os.environ["B200_NO_REFERENCE"] = "1"
+    try:
+        return cpu_baseline(steps, halo, sample, updates)
+    finally:
+        if prev is None:
+            os.environ.pop("B200_NO_REFERENCE", None)
+        else:
+            os.environ["B200_NO_REFERENCE"] = prev
 
 
 P = {"interior_loop": True, "static_pitch": "auto"}
