@@ -300,6 +300,7 @@ class B200Backend(BaseBackend):
         "seq_rotate": {"versioning": True, "type": object},  # "auto" | bool: look-ahead as a register ring instead of a shifting pipeline
         "seq_smem_pad": {"versioning": True, "type": int},  # unused dynamic shared memory per CTA (occupancy cap)
         "thin_tile_j": {"versioning": True, "type": int},  # J tile of one- and two-level sections
+        "halo_lean": {"versioning": True, "type": bool},  # halo_wait kernels: select-based task decode + flag wait without time limit
         "halo_wait": {"versioning": True, "type": bool},  # multi-GPU: boundary tiles wait for the neighbours' pushed halo rows
         "row_pointers": {"versioning": True, "type": bool},
         "fuse_columns": {"versioning": True, "type": bool},
@@ -319,7 +320,7 @@ class B200Backend(BaseBackend):
 
     def codegen_options(self) -> Dict[str, Any]:
         keep = ("strategy", "fmad", "opt_level", "extra_opt_flags", "debug_mode", "tile_j", "warps", "verbose", "vector_width", "prefetch",
-                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait", "uniform_task", "div_inv", "div_slow", "period", "k_order", "col_smem", "col_smem_block", "col_smem_kb", "col_hints", "seq_rotate", "seq_smem_pad", "thin_tile_j")  # fmt: skip
+                "l2_prefetch", "seq_cache", "seq_prefetch", "interior_loop", "static_pitch", "specialize", "stcs", "ldcs", "min_blocks", "fuse_loops", "row_pointers", "fuse_columns", "tma", "tma_rows", "tma_mode", "tma_smem_kb", "halo_wait", "uniform_task", "div_inv", "div_slow", "period", "k_order", "col_smem", "col_smem_block", "col_smem_kb", "col_hints", "seq_rotate", "seq_smem_pad", "thin_tile_j", "halo_lean")  # fmt: skip
         return {k: v for k, v in self.builder.options.backend_opts.items() if k in keep}
 
     def lower(self) -> Dict[str, Any]:

@@ -71,9 +71,7 @@ def install(mp) -> None:
     """mp: a pytest.MonkeyPatch"""
     import torch
 
-    _STATE["installed"] = True
-    mp.setitem(_STATE, "installed", True)  # undone together with the patches
-    _STATE["installed"] = True
+    mp.setitem(_STATE, "installed", True)  # undone together with the patches (the previous value is recorded first)
 
     from gt4py_b200 import runtime, storage
 

@@ -312,10 +312,12 @@ def test_halo_wait_kernels_put_the_boundary_tiles_last_and_wait_for_the_flags():
     flags = (ctypes.c_uint64 * 2)(7, 7)
     addr = ctypes.addressof(flags)
     for opts in ({"halo_wait": True}, {"halo_wait": True, "interior_loop": True, "static_pitch": 160},
-                 {"halo_wait": True, "interior_loop": True, "static_pitch": 160, "tma": 2, "tile_j": 32, "tma_mode": "bulk"}):
+                 {"halo_wait": True, "interior_loop": True, "static_pitch": 160, "tma": 2, "tile_j": 32, "tma_mode": "bulk"},
+                 {"halo_wait": True, "interior_loop": True, "static_pitch": 160, "halo_lean": True}, {"halo_wait": True, "halo_lean": True}):
         es = EmuStencil(st, opts, name="hdiff_halo_wait")
         assert ("fence_proxy_async_global" in es.source) == bool(opts.get("tma"))  # flag acquire (generic proxy) -> bulk copies (async proxy)
         assert "wait_flag" in es.source and "interior tiles first" in es.source
+        assert ("wait_flag_nolimit" in es.source) == bool(opts.get("halo_lean"))
         for hw in ((0, 0, 0), (addr, addr + 8, 7), (addr, 0, 5)):
             got = {k: v.copy() for k, v in fields.items()}
             es.run(got, params, domain, origins, layout="b200", guard="end", halo_wait=hw)
